@@ -1,0 +1,152 @@
+// Host lane emulator: runs the product's lane-level device functions (gypsum_b200/csrc/warp_fft.cuh) with the
+// 32 lanes of each warp as a plain loop, following the same dataflow as kernels.cu (doppler_spectra ->
+// correlate_cells).  Lets the -m "not gpu" suite check the polyphase / padded-FFT algebra and every index map
+// against the oracle without a GPU.  Test infrastructure; never loaded by the product.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../gypsum_b200/csrc/warp_fft.cuh"
+
+using namespace gb;
+
+static std::vector<float2> g_tw1, g_tw2;
+static void init_tables() {
+    if (!g_tw1.empty()) return;
+    g_tw1.resize(1024);
+    g_tw2.resize(1024);
+    for (int k1 = 0; k1 < 32; ++k1)
+        for (int l = 0; l < 32; ++l) {
+            double a = -2.0 * M_PI * ((l * k1) % 1024) / 1024.0;
+            g_tw1[k1 * 32 + l] = make_float2((float)cos(a), (float)sin(a));
+        }
+    for (int n = 0; n < 1024; ++n) {
+        double a = -2.0 * M_PI * n / 2048.0;
+        g_tw2[n] = make_float2((float)cos(a), (float)sin(a));
+    }
+}
+
+struct WarpRegs {
+    float re[32][32], im[32][32];  // [lane][j]
+};
+
+static void warp_fft1024(WarpRegs& w, bool inverse, float2* tile) {
+    for (int lane = 0; lane < 32; ++lane) {
+        if (inverse) wfft_phase1(w.im[lane], w.re[lane], lane, g_tw1.data(), tile);
+        else wfft_phase1(w.re[lane], w.im[lane], lane, g_tw1.data(), tile);
+    }
+    for (int lane = 0; lane < 32; ++lane) {
+        if (inverse) wfft_phase2(w.im[lane], w.re[lane], lane, tile);
+        else wfft_phase2(w.re[lane], w.im[lane], lane, tile);
+    }
+}
+
+extern "C" {
+
+// plain warp FFT-1024 check: x[1024] complex64 in/out (natural order)
+void emu_fft1024(float2* x, int inverse) {
+    init_tables();
+    std::vector<float2> tile(kTileF2);
+    WarpRegs* w = new WarpRegs;
+    for (int lane = 0; lane < 32; ++lane)
+        for (int j = 0; j < 32; ++j) {
+            w->re[lane][j] = x[lane + 32 * j].x;
+            w->im[lane][j] = x[lane + 32 * j].y;
+        }
+    warp_fft1024(*w, inverse != 0, tile.data());
+    for (int lane = 0; lane < 32; ++lane)
+        for (int j = 0; j < 32; ++j) x[lane + 32 * j] = make_float2(w->re[lane][j], w->im[lane][j]);
+    delete w;
+}
+
+// crep[2][1024] for one PRN
+void emu_replica_spectrum(const uint8_t* chips, float2* crep) {
+    std::vector<double2> cs(kPad);
+    for (int t = 0; t < kPad; ++t) cs[t] = make_double2(cos(2.0 * M_PI * t / kPad), sin(2.0 * M_PI * t / kPad));
+    for (int g = 0; g < kPad; ++g) {
+        double re, im;
+        replica_spectrum_bin(chips, g, cs.data(), re, im);
+        crep[(g & 1) * 1024 + (g >> 1)] = make_float2((float)re, (float)im);
+    }
+}
+
+// Full per-cell pipeline.  iq: complex64[n_ms*N]; out: float[N] (non-coherent) or float2[N] (coherent).
+// kind: 1 coherent, 2 non-coherent (utils.py:23-25).
+void emu_cell_profile(const float2* iq, int N, int n_ms, double fs, double doppler, const uint8_t* chips, int kind,
+                      float* out) {
+    init_tables();
+    const int s = N / kChips;
+    std::vector<float2> crep(2048);
+    emu_replica_spectrum(chips, crep.data());
+    std::vector<float2> tile(kTileF2), tileO(kTileF2);
+    std::vector<float2> ypoly((size_t)s * kFft);
+    // spec[i][r][half][1024]
+    std::vector<float2> spec((size_t)n_ms * s * 2 * kFft);
+    WarpRegs* w = new WarpRegs;
+    WarpRegs* wo = new WarpRegs;
+    const double inv_fs = 1.0 / fs;
+    // ---- doppler_spectra ----
+    for (int i = 0; i < n_ms; ++i) {
+        for (int n = 0; n < N; ++n) {
+            const double cyc = doppler * ((double)(n + i * N) * inv_fs);
+            ypoly[(size_t)(n % s) * kFft + n / s] = wipeoff(iq[(size_t)i * N + n], cyc);
+        }
+        for (int t = 0; t < s; ++t) ypoly[(size_t)t * kFft + 1023] = ypoly[(size_t)t * kFft];
+        for (int r = 0; r < s; ++r)
+            for (int half = 0; half < 2; ++half) {
+                for (int lane = 0; lane < 32; ++lane) {
+                    build_z(w->re[lane], w->im[lane], lane, r, s, ypoly.data());
+                    if (half) mul_tw2(w->re[lane], w->im[lane], lane, g_tw2.data());
+                }
+                warp_fft1024(*w, false, tile.data());
+                float2* dst = &spec[(((size_t)i * s + r) * 2 + half) * kFft];
+                for (int lane = 0; lane < 32; ++lane)
+                    for (int j = 0; j < 32; ++j) dst[j * 32 + lane] = make_float2(w->re[lane][j], w->im[lane][j]);
+            }
+    }
+    // ---- correlate_cells ----
+    if (kind == 2) memset(out, 0, sizeof(float) * N);
+    else memset(out, 0, sizeof(float) * 2 * N);
+    const int n_iter = kind == 1 ? 1 : n_ms;
+    for (int r = 0; r < s; ++r) {
+        for (int it = 0; it < n_iter; ++it) {
+            for (int half = 0; half < 2; ++half) {
+                WarpRegs* ww = half ? wo : w;
+                for (int lane = 0; lane < 32; ++lane)
+                    for (int j = 0; j < 32; ++j) {
+                        float2 a = make_float2(0.f, 0.f);
+                        if (kind == 1) {
+                            for (int i = 0; i < n_ms; ++i) {
+                                const float2 v = spec[(((size_t)i * s + r) * 2 + half) * kFft + j * 32 + lane];
+                                a.x += v.x;
+                                a.y += v.y;
+                            }
+                        } else {
+                            a = spec[(((size_t)it * s + r) * 2 + half) * kFft + j * 32 + lane];
+                        }
+                        const float2 y = cmul(a, crep[half * 1024 + j * 32 + lane]);
+                        ww->re[lane][j] = y.x;
+                        ww->im[lane][j] = y.y;
+                    }
+                warp_fft1024(*ww, true, half ? tileO.data() : tile.data());
+                if (half)
+                    for (int lane = 0; lane < 32; ++lane) mul_tw2_conj(ww->re[lane], ww->im[lane], lane, g_tw2.data());
+            }
+            for (int lane = 0; lane < 32; ++lane)
+                for (int j = 0; j < 32; ++j) {
+                    const int q = lane + 32 * j;
+                    if (q >= kChips) continue;
+                    const float xr = w->re[lane][j] + wo->re[lane][j], xi = w->im[lane][j] + wo->im[lane][j];
+                    const int n = s * q + r;
+                    if (kind == 2) out[n] += sqrtf(xr * xr + xi * xi);
+                    else {
+                        out[2 * n] = xr;
+                        out[2 * n + 1] = xi;
+                    }
+                }
+        }
+    }
+    delete w;
+    delete wo;
+}
+}
