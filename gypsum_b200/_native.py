@@ -1,0 +1,179 @@
+"""ctypes binding of include/gypsum_b200.h.  The product path: if the shared library is missing this raises --
+there is no numpy/CPU route behind it."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgypsum_b200.so")
+
+OK, EINVAL, ECUDA, ESTATE = 0, 1, 2, 3
+COHERENT, NON_COHERENT = 1, 2
+
+RECORD_DTYPE = np.dtype(
+    [("peak", "<f4"), ("argmax", "<i4"), ("sum", "<f8"), ("count", "<i4"), ("probe_re", "<f4"), ("probe_im", "<f4"),
+     ("reserved", "<i4")]
+)
+assert RECORD_DTYPE.itemsize == 32
+
+# every symbol include/gypsum_b200.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "gb200_abi_version": (C.c_int, []),
+    "gb200_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "gb200_destroy": (C.c_int, [_P]),
+    "gb200_last_error": (C.c_char_p, [_P]),
+    "gb200_set_stream": (C.c_int, [_P, _P]),
+    "gb200_set_replicas": (C.c_int, [_P, _P, C.c_int]),
+    "gb200_upload_iq": (C.c_int, [_P, _P, C.c_int64]),
+    "gb200_bind_iq_device": (C.c_int, [_P, _P, C.c_int64]),
+    "gb200_acquire_grid": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P]),
+    "gb200_acquire_grid_device": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P]),
+    "gb200_acquire_cells": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "gb200_correlation_profile": (C.c_int, [_P, C.c_int, C.c_double, C.c_int, C.c_int, _P]),
+    "gb200_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+}
+
+_lib = None
+
+
+class NativeLibraryMissing(ImportError):
+    pass
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryMissing(
+                f"{LIB_PATH} is not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(needs nvcc). gypsum_b200 has no CPU fallback."
+            )
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        if lib.gb200_abi_version() != 1:
+            raise ImportError("libgypsum_b200.so ABI version mismatch; rebuild")
+        _lib = lib
+    return _lib
+
+
+def _ptr(a: np.ndarray) -> int:
+    return a.ctypes.data
+
+
+class Engine:
+    """One engine per (device, sample rate).  Thin, exception-raising wrapper over the C ABI."""
+
+    def __init__(self, samples_per_second: int, samples_per_ms: int, device: int = 0):
+        self._lib = load()
+        self._h = _P()
+        rc = self._lib.gb200_create(int(device), int(samples_per_second), int(samples_per_ms), C.byref(self._h))
+        if rc != OK:
+            msg = (self._lib.gb200_last_error(None) or b"").decode()
+            raise (ValueError if rc == EINVAL else RuntimeError)(f"gb200_create: {msg}")
+        self.samples_per_second = int(samples_per_second)
+        self.samples_per_ms = int(samples_per_ms)
+        self.device = int(device)
+        self.n_prn = 0
+
+    # -- plumbing ------------------------------------------------------------------------------------------
+    def _check(self, rc: int, what: str) -> None:
+        if rc == OK:
+            return
+        msg = (self._lib.gb200_last_error(self._h) or b"").decode()
+        raise (ValueError if rc == EINVAL else RuntimeError)(f"{what}: {msg}")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.gb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr: int) -> None:
+        self._check(self._lib.gb200_set_stream(self._h, _P(cuda_stream_ptr or 0)), "gb200_set_stream")
+
+    @property
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        self._check(self._lib.gb200_launch_count(self._h, C.byref(n)), "gb200_launch_count")
+        return n.value
+
+    # -- inputs --------------------------------------------------------------------------------------------
+    def set_replicas(self, chips: np.ndarray) -> None:
+        chips = np.ascontiguousarray(chips, dtype=np.uint8)
+        if chips.ndim != 2 or chips.shape[1] != 1023:
+            raise ValueError("chips must be [n_prn, 1023]")
+        self._check(self._lib.gb200_set_replicas(self._h, _ptr(chips), chips.shape[0]), "gb200_set_replicas")
+        self.n_prn = chips.shape[0]
+
+    def upload_iq(self, samples: np.ndarray) -> None:
+        x = np.ascontiguousarray(samples, dtype=np.complex64)
+        self._iq_keepalive = x
+        self._check(self._lib.gb200_upload_iq(self._h, _ptr(x), x.size), "gb200_upload_iq")
+
+    def upload_iq_ptr(self, host_ptr: int, n_samples: int) -> None:
+        self._check(self._lib.gb200_upload_iq(self._h, _P(host_ptr), n_samples), "gb200_upload_iq")
+
+    def bind_iq_device(self, device_ptr: int, n_samples: int) -> None:
+        self._check(self._lib.gb200_bind_iq_device(self._h, _P(device_ptr), n_samples), "gb200_bind_iq_device")
+
+    # -- the hot path --------------------------------------------------------------------------------------
+    def acquire_grid(self, n_blocks: int, ms_per_block: int, prn_idx, doppler_hz, kind: int = NON_COHERENT) -> np.ndarray:
+        prn = np.ascontiguousarray(prn_idx, dtype=np.int32)
+        dop = np.ascontiguousarray(doppler_hz, dtype=np.float64)
+        out = np.empty((n_blocks, prn.size, dop.size), dtype=RECORD_DTYPE)
+        self._check(
+            self._lib.gb200_acquire_grid(self._h, n_blocks, ms_per_block, _ptr(prn), prn.size, _ptr(dop), dop.size, kind,
+                                         _ptr(out)),
+            "gb200_acquire_grid",
+        )
+        return out
+
+    def acquire_grid_device(self, n_blocks, ms_per_block, prn: np.ndarray, dop: np.ndarray, kind: int, out_device_ptr: int):
+        """prn (int32) / dop (float64) must be contiguous arrays kept alive by the caller; enqueue only."""
+        self._check(
+            self._lib.gb200_acquire_grid_device(self._h, n_blocks, ms_per_block, _ptr(prn), prn.size, _ptr(dop), dop.size,
+                                                kind, _P(out_device_ptr)),
+            "gb200_acquire_grid_device",
+        )
+
+    def acquire_cells(self, prn_idx, doppler_hz, n_ms: int, kind: int = NON_COHERENT, probe_idx=None) -> np.ndarray:
+        prn = np.ascontiguousarray(prn_idx, dtype=np.int32)
+        dop = np.ascontiguousarray(doppler_hz, dtype=np.float64)
+        if prn.shape != dop.shape or prn.ndim != 1:
+            raise ValueError("prn_idx and doppler_hz must be 1-D and the same length")
+        probe = None if probe_idx is None else np.ascontiguousarray(probe_idx, dtype=np.int32)
+        out = np.empty(prn.size, dtype=RECORD_DTYPE)
+        self._check(
+            self._lib.gb200_acquire_cells(self._h, prn.size, _ptr(prn), _ptr(dop), None if probe is None else _ptr(probe),
+                                          n_ms, kind, _ptr(out)),
+            "gb200_acquire_cells",
+        )
+        return out
+
+    def correlation_profile(self, prn_idx: int, doppler_hz: float, n_ms: int, kind: int) -> np.ndarray:
+        n = self.samples_per_ms
+        out = np.empty(n * (2 if kind == COHERENT else 1), dtype=np.float32)
+        self._check(
+            self._lib.gb200_correlation_profile(self._h, int(prn_idx), float(doppler_hz), int(n_ms), int(kind), _ptr(out)),
+            "gb200_correlation_profile",
+        )
+        return out.view(np.complex64) if kind == COHERENT else out
+
+
+def strength_from_records(rec: np.ndarray, n: int) -> np.ndarray:
+    """utils.py:111-116 on the reduced record: peak / mean(profile[profile != peak])."""
+    peak = rec["peak"].astype(np.float64)
+    cnt = rec["count"].astype(np.float64)
+    return peak / ((rec["sum"] - cnt * peak) / (n - cnt))

@@ -1,0 +1,547 @@
+// C ABI of the engine (include/gypsum_b200.h): owns device memory, builds launch plans, drives the kernels.
+// Host side of the reference path it replaces: gypsum/acquisition.py:154-219 (the per-bin scan and its memo
+// wrapper) and gypsum/utils.py:77-108.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/gypsum_b200.h"
+#include "kernels.cuh"
+
+using namespace gb;
+
+static_assert(sizeof(gb200_cell_record) == sizeof(CellRecord), "ABI record and device record must match");
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max(n, static_cast<size_t>(16));
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+template <class T>
+struct PinnedBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max(n, static_cast<size_t>(16));
+        cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&p), want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+}  // namespace
+
+struct gb200_engine {
+    int device = 0, fs = 0, N = 0, s = 0, num_sms = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    DevBuf<float2> tw1, tw2, crep, iq_own, spec;
+    DevBuf<uint8_t> chips;
+    DevBuf<double> d_doppler;
+    DevBuf<int> d_ints;
+    DevBuf<CellRecord> d_records;
+    DevBuf<float> d_profile;
+    PinnedBuf<float2> h_iq;
+    PinnedBuf<CellRecord> h_records;
+    PinnedBuf<int> h_ints;
+    PinnedBuf<double> h_doubles;
+    PinnedBuf<float> h_profile;
+    std::vector<double> doppler_cache;  // what d_doppler[0..] currently holds (grid mode)
+    std::vector<int> prn_cache;         // what d_ints[0..] currently holds (grid mode)
+    bool grid_cache_valid = false;
+    int n_prn = 0;
+    const float2* iq = nullptr;
+    int64_t iq_samples = 0;
+    int64_t launches = 0;
+    size_t spec_budget_bytes = 80u << 20;
+    int np = 8, rsplit_override = 0;
+    std::string err;
+};
+
+#define GB_FAIL(e, code, ...)                        \
+    do {                                             \
+        char buf_[512];                              \
+        snprintf(buf_, sizeof(buf_), __VA_ARGS__);   \
+        (e)->err = buf_;                             \
+        return code;                                 \
+    } while (0)
+
+#define GB_CUDA(e, expr)                                                                                   \
+    do {                                                                                                   \
+        cudaError_t ce_ = (expr);                                                                          \
+        if (ce_ != cudaSuccess) {                                                                          \
+            cudaGetLastError();                                                                            \
+            GB_FAIL(e, GB200_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(ce_), __FILE__, __LINE__); \
+        }                                                                                                  \
+    } while (0)
+
+namespace {
+
+int gcd_int(int a, int b) { return b ? gcd_int(b, a % b) : a; }
+
+int pick_rsplit(const gb200_engine* e) {
+    if (e->rsplit_override > 0 && e->s % e->rsplit_override == 0 && e->np % e->rsplit_override == 0) return e->rsplit_override;
+    return gcd_int(e->s, e->np);
+}
+
+size_t unit_floats2(const gb200_engine* e, int M) { return static_cast<size_t>(M) * e->s * 2 * kFft; }
+
+int check_common(gb200_engine* e, int n_ms, int kind) {
+    if (!e) return GB200_EINVAL;
+    if (kind != GB200_COHERENT && kind != GB200_NON_COHERENT) GB_FAIL(e, GB200_EINVAL, "Unexpected integration type");
+    if (e->n_prn == 0) GB_FAIL(e, GB200_ESTATE, "no PRN replicas loaded (gb200_set_replicas)");
+    if (!e->iq) GB_FAIL(e, GB200_ESTATE, "no IQ loaded (gb200_upload_iq / gb200_bind_iq_device)");
+    if (n_ms < 1) GB_FAIL(e, GB200_EINVAL, "need at least one whole millisecond of samples");
+    return GB200_OK;
+}
+
+// grid mode: all cells of n_blocks x prn list x doppler list; records written to rec_dev (device)
+int run_grid(gb200_engine* e, int n_blocks, int M, const int32_t* prn_idx, int P, const double* dop, int D, int kind,
+             CellRecord* rec_dev) {
+    int rc = check_common(e, M, kind);
+    if (rc) return rc;
+    if (n_blocks < 1 || P < 1 || D < 1 || !prn_idx || !dop) GB_FAIL(e, GB200_EINVAL, "empty grid");
+    if (static_cast<int64_t>(n_blocks) * M * e->N > e->iq_samples)
+        GB_FAIL(e, GB200_EINVAL, "grid needs %lld samples, %lld loaded", static_cast<long long>(n_blocks) * M * e->N,
+                static_cast<long long>(e->iq_samples));
+    for (int i = 0; i < P; ++i)
+        if (prn_idx[i] < 0 || prn_idx[i] >= e->n_prn) GB_FAIL(e, GB200_EINVAL, "prn index %d out of range", prn_idx[i]);
+
+    // (re)upload the axes only when they changed
+    const bool same = e->grid_cache_valid && static_cast<int>(e->doppler_cache.size()) == D &&
+                      static_cast<int>(e->prn_cache.size()) == P &&
+                      memcmp(e->doppler_cache.data(), dop, sizeof(double) * D) == 0 &&
+                      memcmp(e->prn_cache.data(), prn_idx, sizeof(int) * P) == 0;
+    if (!same) {
+        GB_CUDA(e, cudaStreamSynchronize(e->stream));  // staging buffers may still be in flight
+        GB_CUDA(e, e->d_doppler.ensure(D));
+        GB_CUDA(e, e->d_ints.ensure(P));
+        GB_CUDA(e, e->h_doubles.ensure(D));
+        GB_CUDA(e, e->h_ints.ensure(P));
+        memcpy(e->h_doubles.p, dop, sizeof(double) * D);
+        memcpy(e->h_ints.p, prn_idx, sizeof(int) * P);
+        GB_CUDA(e, cudaMemcpyAsync(e->d_doppler.p, e->h_doubles.p, sizeof(double) * D, cudaMemcpyHostToDevice, e->stream));
+        GB_CUDA(e, cudaMemcpyAsync(e->d_ints.p, e->h_ints.p, sizeof(int) * P, cudaMemcpyHostToDevice, e->stream));
+        e->doppler_cache.assign(dop, dop + D);
+        e->prn_cache.assign(prn_idx, prn_idx + P);
+        e->grid_cache_valid = true;
+    }
+
+    const size_t unit = unit_floats2(e, M);
+    const size_t per_block = unit * D;
+    int nb = static_cast<int>(std::max<size_t>(1, e->spec_budget_bytes / (per_block * sizeof(float2))));
+    nb = std::min(nb, n_blocks);
+    GB_CUDA(e, e->spec.ensure(per_block * nb));
+
+    const int rsplit = pick_rsplit(e);
+    const int cpg = e->np / rsplit;
+    const int chunks = (D + cpg - 1) / cpg;
+    for (int b0 = 0; b0 < n_blocks; b0 += nb) {
+        const int nbb = std::min(nb, n_blocks - b0);
+        SpectraArgs sa{};
+        sa.iq = e->iq + static_cast<size_t>(b0) * M * e->N;
+        sa.doppler = e->d_doppler.p;
+        sa.spec = e->spec.p;
+        sa.tw1 = e->tw1.p;
+        sa.tw2 = e->tw2.p;
+        sa.block_stride = static_cast<long long>(M) * e->N;
+        sa.inv_fs = 1.0 / static_cast<double>(e->fs);
+        sa.N = e->N;
+        sa.s = e->s;
+        sa.M = M;
+        sa.n_doppler = D;
+        sa.n_units = nbb * D;
+        GB_CUDA(e, launch_doppler_spectra(sa, e->stream));
+        e->launches++;
+
+        CorrelateArgs ca{};
+        ca.spec = e->spec.p;
+        ca.crep = e->crep.p;
+        ca.tw1 = e->tw1.p;
+        ca.tw2 = e->tw2.p;
+        ca.records = rec_dev + static_cast<size_t>(b0) * P * D;
+        ca.profile = nullptr;
+        ca.N = e->N;
+        ca.s = e->s;
+        ca.M = M;
+        ca.kind = kind;
+        ca.rsplit = rsplit;
+        ca.n_groups = nbb * P * chunks;
+        ca.grid_mode = 1;
+        ca.P = P;
+        ca.D = D;
+        ca.chunks = chunks;
+        ca.prn_idx = e->d_ints.p;
+        ca.cell_probe = nullptr;
+        const int grid = std::min(ca.n_groups, e->num_sms * (e->np == 8 ? 1 : 2));
+        GB_CUDA(e, launch_correlate_cells(ca, e->np, grid, e->stream));
+        e->launches++;
+    }
+    return GB200_OK;
+}
+
+// list mode.  Cells are sorted by PRN and cut into chunks whose spectra fit the scratch budget.
+int run_cells(gb200_engine* e, int n_cells, const int32_t* prn_idx, const double* dop, const int32_t* probe, int M,
+              int kind, CellRecord* rec_dev, float* profile_dev) {
+    int rc = check_common(e, M, kind);
+    if (rc) return rc;
+    if (n_cells < 1 || !prn_idx || !dop) GB_FAIL(e, GB200_EINVAL, "empty cell list");
+    if (static_cast<int64_t>(M) * e->N > e->iq_samples)
+        GB_FAIL(e, GB200_EINVAL, "need %lld samples, %lld loaded", static_cast<long long>(M) * e->N,
+                static_cast<long long>(e->iq_samples));
+    for (int i = 0; i < n_cells; ++i)
+        if (prn_idx[i] < 0 || prn_idx[i] >= e->n_prn) GB_FAIL(e, GB200_EINVAL, "prn index %d out of range", prn_idx[i]);
+    e->grid_cache_valid = false;  // d_ints / d_doppler are about to be overwritten
+
+    const int rsplit = pick_rsplit(e);
+    const int cpg = e->np / rsplit;
+    std::vector<int> order(n_cells);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return prn_idx[a] < prn_idx[b]; });
+
+    const size_t unit = unit_floats2(e, M);
+    const int max_cells = static_cast<int>(std::max<size_t>(cpg, e->spec_budget_bytes / (unit * sizeof(float2)) / cpg * cpg));
+
+    GB_CUDA(e, cudaStreamSynchronize(e->stream));
+    // probe indices live at the front of the int buffer for the whole call
+    const size_t ints_needed = static_cast<size_t>(n_cells) * 3 + 3 * (static_cast<size_t>(n_cells) + 1);
+    GB_CUDA(e, e->d_ints.ensure(ints_needed));
+    GB_CUDA(e, e->h_ints.ensure(ints_needed));
+    GB_CUDA(e, e->d_doppler.ensure(n_cells));
+    GB_CUDA(e, e->h_doubles.ensure(n_cells));
+    for (int i = 0; i < n_cells; ++i) e->h_ints.p[i] = probe ? probe[i] : -1;
+    GB_CUDA(e, cudaMemcpyAsync(e->d_ints.p, e->h_ints.p, sizeof(int) * n_cells, cudaMemcpyHostToDevice, e->stream));
+    GB_CUDA(e, e->spec.ensure(unit * std::min(max_cells, n_cells)));
+
+    int c0 = 0;
+    while (c0 < n_cells) {
+        // take up to max_cells sorted cells, ending on a PRN-group boundary where possible
+        int c1 = std::min(n_cells, c0 + max_cells);
+        // plan arrays for this chunk (indices into the chunk)
+        std::map<double, int> uniq;
+        std::vector<double> udop;
+        std::vector<int> cell_u, cell_out, g_first, g_count, g_prn;
+        for (int c = c0; c < c1; ++c) {
+            const int orig = order[c];
+            auto it = uniq.find(dop[orig]);
+            int u;
+            if (it == uniq.end()) {
+                u = static_cast<int>(udop.size());
+                uniq.emplace(dop[orig], u);
+                udop.push_back(dop[orig]);
+            } else {
+                u = it->second;
+            }
+            cell_u.push_back(u);
+            cell_out.push_back(orig);
+            if (g_prn.empty() || g_prn.back() != prn_idx[orig] || g_count.back() == cpg) {
+                g_first.push_back(c - c0);
+                g_count.push_back(1);
+                g_prn.push_back(prn_idx[orig]);
+            } else {
+                g_count.back()++;
+            }
+        }
+        const int nc = c1 - c0, ng = static_cast<int>(g_prn.size()), nu = static_cast<int>(udop.size());
+        // the staging buffers are reused per chunk: wait for the previous chunk's copies
+        if (c0 > 0) GB_CUDA(e, cudaStreamSynchronize(e->stream));
+        int* hi = e->h_ints.p + n_cells;
+        int* di = e->d_ints.p + n_cells;
+        memcpy(hi, cell_u.data(), sizeof(int) * nc);
+        memcpy(hi + nc, cell_out.data(), sizeof(int) * nc);
+        memcpy(hi + 2 * nc, g_first.data(), sizeof(int) * ng);
+        memcpy(hi + 2 * nc + ng, g_count.data(), sizeof(int) * ng);
+        memcpy(hi + 2 * nc + 2 * ng, g_prn.data(), sizeof(int) * ng);
+        memcpy(e->h_doubles.p, udop.data(), sizeof(double) * nu);
+        GB_CUDA(e, cudaMemcpyAsync(di, hi, sizeof(int) * (2 * nc + 3 * ng), cudaMemcpyHostToDevice, e->stream));
+        GB_CUDA(e, cudaMemcpyAsync(e->d_doppler.p, e->h_doubles.p, sizeof(double) * nu, cudaMemcpyHostToDevice, e->stream));
+
+        SpectraArgs sa{};
+        sa.iq = e->iq;
+        sa.doppler = e->d_doppler.p;
+        sa.spec = e->spec.p;
+        sa.tw1 = e->tw1.p;
+        sa.tw2 = e->tw2.p;
+        sa.block_stride = 0;
+        sa.inv_fs = 1.0 / static_cast<double>(e->fs);
+        sa.N = e->N;
+        sa.s = e->s;
+        sa.M = M;
+        sa.n_doppler = nu;
+        sa.n_units = nu;
+        GB_CUDA(e, launch_doppler_spectra(sa, e->stream));
+        e->launches++;
+
+        CorrelateArgs ca{};
+        ca.spec = e->spec.p;
+        ca.crep = e->crep.p;
+        ca.tw1 = e->tw1.p;
+        ca.tw2 = e->tw2.p;
+        ca.records = rec_dev;
+        ca.profile = profile_dev;
+        ca.N = e->N;
+        ca.s = e->s;
+        ca.M = M;
+        ca.kind = kind;
+        ca.rsplit = rsplit;
+        ca.n_groups = ng;
+        ca.grid_mode = 0;
+        ca.cell_u = di;
+        ca.cell_out = di + nc;
+        ca.grp_first = di + 2 * nc;
+        ca.grp_count = di + 2 * nc + ng;
+        ca.grp_prn = di + 2 * nc + 2 * ng;
+        ca.cell_probe = e->d_ints.p;
+        const int grid = std::min(ng, e->num_sms * (e->np == 8 ? 1 : 2));
+        GB_CUDA(e, launch_correlate_cells(ca, e->np, grid, e->stream));
+        e->launches++;
+        c0 = c1;
+    }
+    return GB200_OK;
+}
+
+int fetch_records(gb200_engine* e, size_t n, gb200_cell_record* out_host) {
+    GB_CUDA(e, e->h_records.ensure(n));
+    GB_CUDA(e, cudaMemcpyAsync(e->h_records.p, e->d_records.p, n * sizeof(CellRecord), cudaMemcpyDeviceToHost, e->stream));
+    GB_CUDA(e, cudaStreamSynchronize(e->stream));
+    memcpy(out_host, e->h_records.p, n * sizeof(CellRecord));
+    return GB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gb200_abi_version(void) { return GB200_ABI_VERSION; }
+
+const char* gb200_last_error(const gb200_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int gb200_create(int device, int fs, int n, gb200_engine** out) {
+    if (!out) return GB200_EINVAL;
+    *out = nullptr;
+    if (n <= 0 || n % kChips != 0 || fs <= 0) {
+        g_create_error = "samples_per_ms must be a positive multiple of 1023 and samples_per_second positive";
+        return GB200_EINVAL;
+    }
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || device < 0 || device >= count) {
+        cudaGetLastError();
+        g_create_error = std::string("no usable CUDA device (there is no CPU fallback): ") +
+                         (ce != cudaSuccess ? cudaGetErrorString(ce) : "ordinal out of range");
+        return GB200_ECUDA;
+    }
+    gb200_engine* e = new gb200_engine;
+    e->device = device;
+    e->fs = fs;
+    e->N = n;
+    e->s = n / kChips;
+    e->spec_budget_bytes = static_cast<size_t>(env_int("GB200_SPEC_BUDGET_MB", 80)) << 20;
+    e->np = env_int("GB200_NP", 8) == 4 ? 4 : 8;
+    e->rsplit_override = env_int("GB200_RSPLIT", 0);
+    auto fail = [&](cudaError_t c, const char* what) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(c);
+        cudaGetLastError();
+        delete e;
+        return GB200_ECUDA;
+    };
+    if ((ce = cudaSetDevice(device)) != cudaSuccess) return fail(ce, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(ce, "cudaGetDeviceProperties");
+    if (prop.major != 10) {
+        g_create_error = "this build targets sm_100a (B200) only";
+        delete e;
+        return GB200_ECUDA;
+    }
+    e->num_sms = prop.multiProcessorCount;
+    if (spectra_smem_bytes(e->s) > 200 * 1024) {
+        g_create_error = "samples_per_ms too large for the shared-memory polyphase buffer";
+        delete e;
+        return GB200_EINVAL;
+    }
+    if ((ce = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(ce, "cudaStreamCreate");
+    e->stream = e->own_stream;
+    if ((ce = configure_kernels()) != cudaSuccess) return fail(ce, "cudaFuncSetAttribute");
+    if ((ce = e->tw1.ensure(kFft)) != cudaSuccess) return fail(ce, "cudaMalloc");
+    if ((ce = e->tw2.ensure(kFft)) != cudaSuccess) return fail(ce, "cudaMalloc");
+    if ((ce = launch_init_tables(e->tw1.p, e->tw2.p, e->stream)) != cudaSuccess) return fail(ce, "init_tables");
+    e->launches++;
+    if ((ce = cudaStreamSynchronize(e->stream)) != cudaSuccess) return fail(ce, "init_tables sync");
+    *out = e;
+    return GB200_OK;
+}
+
+int gb200_destroy(gb200_engine* e) {
+    if (!e) return GB200_OK;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    e->tw1.release();
+    e->tw2.release();
+    e->crep.release();
+    e->iq_own.release();
+    e->spec.release();
+    e->chips.release();
+    e->d_doppler.release();
+    e->d_ints.release();
+    e->d_records.release();
+    e->d_profile.release();
+    e->h_iq.release();
+    e->h_records.release();
+    e->h_ints.release();
+    e->h_doubles.release();
+    e->h_profile.release();
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+    return GB200_OK;
+}
+
+int gb200_set_stream(gb200_engine* e, void* st) {
+    if (!e) return GB200_EINVAL;
+    GB_CUDA(e, cudaSetDevice(e->device));
+    GB_CUDA(e, cudaStreamSynchronize(e->stream));
+    e->stream = st ? static_cast<cudaStream_t>(st) : e->own_stream;
+    return GB200_OK;
+}
+
+int gb200_set_replicas(gb200_engine* e, const uint8_t* chips, int n_prn) {
+    if (!e) return GB200_EINVAL;
+    if (!chips || n_prn < 1) GB_FAIL(e, GB200_EINVAL, "need at least one PRN code");
+    for (int i = 0; i < n_prn * kChips; ++i)
+        if (chips[i] > 1) GB_FAIL(e, GB200_EINVAL, "chips must be 0 or 1");
+    GB_CUDA(e, cudaSetDevice(e->device));
+    GB_CUDA(e, cudaStreamSynchronize(e->stream));
+    GB_CUDA(e, e->chips.ensure(static_cast<size_t>(n_prn) * kChips));
+    GB_CUDA(e, e->crep.ensure(static_cast<size_t>(n_prn) * 2 * kFft));
+    GB_CUDA(e, cudaMemcpyAsync(e->chips.p, chips, static_cast<size_t>(n_prn) * kChips, cudaMemcpyHostToDevice, e->stream));
+    GB_CUDA(e, launch_replica_spectra(e->chips.p, n_prn, e->crep.p, e->stream));
+    e->launches++;
+    GB_CUDA(e, cudaStreamSynchronize(e->stream));
+    e->n_prn = n_prn;
+    return GB200_OK;
+}
+
+int gb200_upload_iq(gb200_engine* e, const float* iq_host, int64_t n_samples) {
+    if (!e) return GB200_EINVAL;
+    if (!iq_host || n_samples < 0) GB_FAIL(e, GB200_EINVAL, "bad IQ buffer");
+    GB_CUDA(e, cudaSetDevice(e->device));
+    GB_CUDA(e, e->iq_own.ensure(static_cast<size_t>(std::max<int64_t>(n_samples, 1))));
+    const void* src = iq_host;
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, iq_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (!pinned) {
+        GB_CUDA(e, cudaStreamSynchronize(e->stream));  // staging buffer may still be in flight
+        GB_CUDA(e, e->h_iq.ensure(static_cast<size_t>(std::max<int64_t>(n_samples, 1))));
+        memcpy(e->h_iq.p, iq_host, static_cast<size_t>(n_samples) * sizeof(float2));
+        src = e->h_iq.p;
+    }
+    GB_CUDA(e, cudaMemcpyAsync(e->iq_own.p, src, static_cast<size_t>(n_samples) * sizeof(float2), cudaMemcpyHostToDevice,
+                               e->stream));
+    e->iq = e->iq_own.p;
+    e->iq_samples = n_samples;
+    return GB200_OK;
+}
+
+int gb200_bind_iq_device(gb200_engine* e, const void* iq_device, int64_t n_samples) {
+    if (!e) return GB200_EINVAL;
+    if (!iq_device || n_samples < 0) GB_FAIL(e, GB200_EINVAL, "bad IQ buffer");
+    if (reinterpret_cast<uintptr_t>(iq_device) % 8 != 0) GB_FAIL(e, GB200_EINVAL, "IQ buffer must be 8-byte aligned");
+    e->iq = static_cast<const float2*>(iq_device);
+    e->iq_samples = n_samples;
+    return GB200_OK;
+}
+
+int gb200_acquire_grid_device(gb200_engine* e, int n_blocks, int M, const int32_t* prn_idx, int P, const double* dop, int D,
+                              int kind, void* out_device) {
+    if (!e) return GB200_EINVAL;
+    if (!out_device) GB_FAIL(e, GB200_EINVAL, "null output");
+    GB_CUDA(e, cudaSetDevice(e->device));
+    return run_grid(e, n_blocks, M, prn_idx, P, dop, D, kind, static_cast<CellRecord*>(out_device));
+}
+
+int gb200_acquire_grid(gb200_engine* e, int n_blocks, int M, const int32_t* prn_idx, int P, const double* dop, int D,
+                       int kind, gb200_cell_record* out_host) {
+    if (!e) return GB200_EINVAL;
+    if (!out_host) GB_FAIL(e, GB200_EINVAL, "null output");
+    GB_CUDA(e, cudaSetDevice(e->device));
+    if (n_blocks < 1 || P < 1 || D < 1) GB_FAIL(e, GB200_EINVAL, "empty grid");
+    const size_t n = static_cast<size_t>(n_blocks) * P * D;
+    GB_CUDA(e, e->d_records.ensure(n));
+    int rc = run_grid(e, n_blocks, M, prn_idx, P, dop, D, kind, e->d_records.p);
+    if (rc) return rc;
+    return fetch_records(e, n, out_host);
+}
+
+int gb200_acquire_cells(gb200_engine* e, int n_cells, const int32_t* prn_idx, const double* dop, const int32_t* probe,
+                        int n_ms, int kind, gb200_cell_record* out_host) {
+    if (!e) return GB200_EINVAL;
+    if (!out_host) GB_FAIL(e, GB200_EINVAL, "null output");
+    GB_CUDA(e, cudaSetDevice(e->device));
+    if (n_cells < 1) GB_FAIL(e, GB200_EINVAL, "empty cell list");
+    GB_CUDA(e, e->d_records.ensure(n_cells));
+    int rc = run_cells(e, n_cells, prn_idx, dop, probe, n_ms, kind, e->d_records.p, nullptr);
+    if (rc) return rc;
+    return fetch_records(e, n_cells, out_host);
+}
+
+int gb200_correlation_profile(gb200_engine* e, int prn, double dop, int n_ms, int kind, float* out_host) {
+    if (!e) return GB200_EINVAL;
+    if (!out_host) GB_FAIL(e, GB200_EINVAL, "null output");
+    GB_CUDA(e, cudaSetDevice(e->device));
+    const size_t nf = static_cast<size_t>(e->N) * (kind == GB200_COHERENT ? 2 : 1);
+    GB_CUDA(e, e->d_profile.ensure(nf));
+    GB_CUDA(e, e->h_profile.ensure(nf));
+    GB_CUDA(e, e->d_records.ensure(1));
+    const int32_t p = prn;
+    int rc = run_cells(e, 1, &p, &dop, nullptr, n_ms, kind, e->d_records.p, e->d_profile.p);
+    if (rc) return rc;
+    GB_CUDA(e, cudaMemcpyAsync(e->h_profile.p, e->d_profile.p, nf * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    GB_CUDA(e, cudaStreamSynchronize(e->stream));
+    memcpy(out_host, e->h_profile.p, nf * sizeof(float));
+    return GB200_OK;
+}
+
+int gb200_launch_count(const gb200_engine* e, int64_t* out) {
+    if (!e || !out) return GB200_EINVAL;
+    *out = e->launches;
+    return GB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,435 @@
+// sm_100a kernels of the acquisition correlation path (reference: gypsum/utils.py:59-116 driven by
+// gypsum/acquisition.py:154-190).  No cuFFT, no tensor cores, no CPU fallback.
+//
+//   doppler_spectra   per (Doppler, ms): carrier wipe-off (utils.py:93-97), polyphase boxcar, forward warp FFTs.
+//                     This half of utils.py:65 does not depend on the PRN, so it is computed once per Doppler
+//                     bin and shared by all PRNs instead of being redone per cell as the reference does.
+//   correlate_cells   per (PRN, Doppler) cell: x conj(FFT(replica)) (utils.py:69, spectrum staged into shared
+//                     memory with a TMA bulk copy), inverse warp FFTs (utils.py:73), |.| accumulation over ms
+//                     (utils.py:102-104) in registers, peak/argmax/sum/count reduction with warp shuffles
+//                     (acquisition.py:181-189, utils.py:111-116).
+#include "kernels.cuh"
+#include "warp_fft.cuh"
+
+namespace gb {
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D TMA bulk copy (global -> shared), named barriers.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void pair_barrier(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); }
+
+// ---------------------------------------------------------------------------------------------------------
+// One-time setup
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_init_tables(float2* tw1, float2* tw2) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;  // 0..1023
+    if (t >= 1024) return;
+    {
+        const int k1 = t >> 5, l = t & 31;
+        double s, c;
+        sincospi(-2.0 * ((l * k1) & 1023) / 1024.0, &s, &c);
+        tw1[t] = make_float2(static_cast<float>(c), static_cast<float>(s));
+    }
+    {
+        double s, c;
+        sincospi(-2.0 * t / 2048.0, &s, &c);
+        tw2[t] = make_float2(static_cast<float>(c), static_cast<float>(s));
+    }
+}
+
+// crep[p][g&1][g>>1] = conj(FFT2048(c'_p))[g] / 2048, direct float64 DFT with an exact-phase table (one-time;
+// the reference instead recomputes np.fft.fft(prn_replica) on every call, utils.py:66).
+__global__ void __launch_bounds__(128) k_replica_spectra(const uint8_t* chips, float2* crep) {
+    __shared__ double2 cs[kPad];
+    __shared__ uint8_t c[1024];
+    const int p = blockIdx.y;
+    for (int t = threadIdx.x; t < kPad; t += blockDim.x) {
+        double s, co;
+        sincospi(2.0 * t / kPad, &s, &co);
+        cs[t] = make_double2(co, s);
+    }
+    for (int t = threadIdx.x; t < kChips; t += blockDim.x) c[t] = chips[p * kChips + t];
+    __syncthreads();
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    double re, im;
+    replica_spectrum_bin(c, g, cs, re, im);
+    crep[(static_cast<size_t>(p) * 2 + (g & 1)) * kFft + (g >> 1)] = make_float2(static_cast<float>(re), static_cast<float>(im));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// doppler_spectra
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kSpecWarps = 4;
+
+__global__ void __launch_bounds__(kSpecWarps * 32) k_doppler_spectra(const SpectraArgs a) {
+    const float2* __restrict__ tw1 = a.tw1;
+    const float2* __restrict__ tw2 = a.tw2;
+    extern __shared__ __align__(16) float2 smem[];
+    float2* ypoly = smem;                                   // [s][1024]
+    float2* tiles = smem + static_cast<size_t>(a.s) * kFft;  // [kSpecWarps][kTileF2]
+
+    const int unit = blockIdx.x / a.M, i = blockIdx.x % a.M;
+    const int b = unit / a.n_doppler, d = unit % a.n_doppler;
+    const double f = a.doppler[d];
+    const float2* __restrict__ src = a.iq + static_cast<size_t>(b) * a.block_stride + static_cast<size_t>(i) * a.N;
+
+    // Wipe-off, coalesced float2 loads of the 1-ms IQ vector; stored de-interleaved by polyphase branch.
+    for (int n = threadIdx.x; n < a.N; n += blockDim.x) {
+        const float2 x = src[n];
+        const double cyc = f * (static_cast<double>(n + i * a.N) * a.inv_fs);
+        const int row = n % a.s, col = n / a.s;
+        ypoly[row * kFft + col] = wipeoff(x, cyc);
+    }
+    __syncthreads();
+    if (threadIdx.x < a.s) ypoly[threadIdx.x * kFft + (kFft - 1)] = ypoly[threadIdx.x * kFft];
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float2* tile = tiles + warp * kTileF2;
+    float2* __restrict__ dst0 = a.spec + (static_cast<size_t>(unit) * a.M + i) * a.s * 2 * kFft;
+    for (int task = warp; task < 2 * a.s; task += kSpecWarps) {
+        const int r = task >> 1, half = task & 1;
+        float re[32], im[32];
+        build_z(re, im, lane, r, a.s, ypoly);
+        if (half) mul_tw2(re, im, lane, tw2);
+        wfft_phase1(re, im, lane, tw1, tile);
+        __syncwarp();
+        wfft_phase2(re, im, lane, tile);
+        __syncwarp();
+        float2* __restrict__ dst = dst0 + static_cast<size_t>(task) * kFft;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dst[j * 32 + lane] = make_float2(re[j], im[j]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// correlate_cells
+// ---------------------------------------------------------------------------------------------------------
+struct PairPartial {  // exchanged through shared memory when several pairs share a cell
+    float mx;
+    int idx;
+    int cnt;
+    float pr_re;
+    double sum;
+    float pr_im;
+    int pad;
+};
+
+__device__ __forceinline__ void warp_reduce_peak(Peak& p) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        Peak o;
+        o.mx = __shfl_xor_sync(0xffffffffu, p.mx, off);
+        o.idx = __shfl_xor_sync(0xffffffffu, p.idx, off);
+        o.cnt = __shfl_xor_sync(0xffffffffu, p.cnt, off);
+        o.sum = __shfl_xor_sync(0xffffffffu, p.sum, off);
+        peak_merge(p, o);
+    }
+}
+
+template <int NP, int KIND>
+__global__ void __launch_bounds__(NP * 64, (NP == 8 ? 1 : 2)) k_correlate_cells(const CorrelateArgs a) {
+    extern __shared__ __align__(16) float2 smem[];
+    float2* crep_s = smem;                 // [2][1024]
+    float2* tw1_s = crep_s + 2 * kFft;     // [32][32]
+    float2* tw2_s = tw1_s + kFft;          // [1024]
+    float2* tiles = tw2_s + kFft;          // [2*NP][kTileF2]
+    PairPartial* partial = reinterpret_cast<PairPartial*>(tiles + 2 * NP * kTileF2);  // [NP][2]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(partial + 2 * NP);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = warp >> 1, h = warp & 1;
+    float2* tile = tiles + warp * kTileF2;
+    const float2* ptile = tiles + (warp ^ 1) * kTileF2;
+
+    uint32_t parity = 0;
+    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(mbar, 2 * kFft * sizeof(float2));
+        bulk_g2s(tw1_s, a.tw1, kFft * sizeof(float2), mbar);
+        bulk_g2s(tw2_s, a.tw2, kFft * sizeof(float2), mbar);
+    }
+    mbar_wait(mbar, parity);
+    parity ^= 1;
+
+    const int cells_per_group = NP / a.rsplit;
+    const int r_per_pair = a.s / a.rsplit;
+    const int my_cell = pair / a.rsplit;          // cell slot inside the group
+    const int my_r0 = (pair % a.rsplit) * r_per_pair;
+    const size_t unit_stride = static_cast<size_t>(a.M) * a.s * 2 * kFft;
+    int cur_prn = -1;
+
+    for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x) {
+        // ---- decode the group (uniform across the CTA) ----
+        int prn, n_cells, unit = 0, out = 0;
+        if (a.grid_mode) {
+            const int per_block = a.P * a.chunks;
+            const int b = g / per_block, rem = g % per_block;
+            const int pl = rem / a.chunks, ch = rem % a.chunks;
+            prn = a.prn_idx[pl];
+            n_cells = min(cells_per_group, a.D - ch * cells_per_group);
+            const int d = ch * cells_per_group + my_cell;
+            unit = b * a.D + d;
+            out = (b * a.P + pl) * a.D + d;
+        } else {
+            prn = a.grp_prn[g];
+            n_cells = a.grp_count[g];
+            if (my_cell < n_cells) {
+                const int c = a.grp_first[g] + my_cell;
+                unit = a.cell_u[c];
+                out = a.cell_out[c];
+            }
+        }
+        const bool active = my_cell < n_cells;
+
+        // ---- stage conj(FFT(replica)) of this PRN: TMA bulk copy into shared memory ----
+        if (prn != cur_prn) {
+            __syncthreads();  // everyone is done with the previous replica
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(mbar, 2 * kFft * sizeof(float2));
+                bulk_g2s(crep_s, a.crep + static_cast<size_t>(prn) * 2 * kFft, 2 * kFft * sizeof(float2), mbar);
+            }
+            mbar_wait(mbar, parity);
+            parity ^= 1;
+            cur_prn = prn;
+        }
+
+        Peak pk;
+        peak_init(pk);
+        float pr_re = 0.f, pr_im = 0.f;
+        if (active) {
+            const int probe = (KIND == kKindCoherent && a.cell_probe) ? a.cell_probe[out] : -1;
+            const float2* __restrict__ spec_u = a.spec + static_cast<size_t>(unit) * unit_stride;
+            const float2* crep_h = crep_s + h * kFft;
+            float* prof = a.profile;
+            for (int r = my_r0; r < my_r0 + r_per_pair; ++r) {
+                float acc[16];
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) acc[jj] = 0.f;
+                const int n_iter = (KIND == kKindCoherent) ? 1 : a.M;
+                for (int it = 0; it < n_iter; ++it) {
+                    float re[32], im[32];
+                    if (KIND == kKindCoherent) {
+                        // Coherent integration (utils.py:102) commutes with the linear correlation: sum the
+                        // M spectra first, transform once.
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) re[j] = im[j] = 0.f;
+                        for (int i = 0; i < a.M; ++i) {
+                            const float2* __restrict__ p = spec_u + (static_cast<size_t>(i * a.s + r) * 2 + h) * kFft;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float2 v = p[j * 32 + lane];
+                                re[j] += v.x;
+                                im[j] += v.y;
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float2 y = cmul(make_float2(re[j], im[j]), crep_h[j * 32 + lane]);
+                            re[j] = y.x;
+                            im[j] = y.y;
+                        }
+                    } else {
+                        const float2* __restrict__ p = spec_u + (static_cast<size_t>(it * a.s + r) * 2 + h) * kFft;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float2 y = cmul(p[j * 32 + lane], crep_h[j * 32 + lane]);
+                            re[j] = y.x;
+                            im[j] = y.y;
+                        }
+                    }
+                    // inverse warp FFT-1024 = forward transform on swapped re/im
+                    wfft_phase1(im, re, lane, tw1_s, tile);
+                    __syncwarp();
+                    wfft_phase2(im, re, lane, tile);
+                    __syncwarp();
+                    if (h) mul_tw2_conj(re, im, lane, tw2_s);
+                    // out[k] = E[k] + W2048^-k O[k]: the even-bin warp finishes lags [0,512), the odd-bin
+                    // warp lags [512,1024); each hands the other half over through its (now idle) tile.
+                    if (h == 0) {
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) tile[jj * 32 + lane] = make_float2(re[16 + jj], im[16 + jj]);
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) tile[jj * 32 + lane] = make_float2(re[jj], im[jj]);
+                    }
+                    pair_barrier(pair);
+                    float xr[16], xi[16];
+                    if (h == 0) {
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) {
+                            const float2 o = ptile[jj * 32 + lane];
+                            xr[jj] = re[jj] + o.x;
+                            xi[jj] = im[jj] + o.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) {
+                            const float2 o = ptile[jj * 32 + lane];
+                            xr[jj] = re[16 + jj] + o.x;
+                            xi[jj] = im[16 + jj] + o.y;
+                        }
+                    }
+                    if (KIND == kKindCoherent) {
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) {
+                            acc[jj] = sqrtf(xr[jj] * xr[jj] + xi[jj] * xi[jj]);
+                            const int q = lane + 32 * (16 * h + jj);
+                            const int n = a.s * q + r;
+                            if (q < kChips) {
+                                if (n == probe) {
+                                    pr_re = xr[jj];
+                                    pr_im = xi[jj];
+                                }
+                                if (prof) {
+                                    prof[2 * n] = xr[jj];
+                                    prof[2 * n + 1] = xi[jj];
+                                }
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) acc[jj] += sqrtf(xr[jj] * xr[jj] + xi[jj] * xi[jj]);
+                    }
+                    pair_barrier(pair);  // partner has read my tile; the next phase 1 may overwrite it
+                }
+                float psum = 0.f;
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) {
+                    const int q = lane + 32 * (16 * h + jj);
+                    if (q < kChips) {
+                        const int n = a.s * q + r;
+                        peak_push(pk, acc[jj], n);
+                        psum += acc[jj];
+                        if (prof && KIND != kKindCoherent) prof[n] = acc[jj];
+                    }
+                }
+                pk.sum += static_cast<double>(psum);
+            }
+            warp_reduce_peak(pk);
+            pr_re += __shfl_xor_sync(0xffffffffu, pr_re, 16);
+            pr_im += __shfl_xor_sync(0xffffffffu, pr_im, 16);
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) {
+                pr_re += __shfl_xor_sync(0xffffffffu, pr_re, off);
+                pr_im += __shfl_xor_sync(0xffffffffu, pr_im, off);
+            }
+            if (lane == 0) {
+                PairPartial pp;
+                pp.mx = pk.mx;
+                pp.idx = pk.idx;
+                pp.cnt = pk.cnt;
+                pp.sum = pk.sum;
+                pp.pr_re = pr_re;
+                pp.pr_im = pr_im;
+                pp.pad = 0;
+                partial[warp] = pp;
+            }
+        }
+        __syncthreads();
+        // first warp of each cell merges the 2*rsplit partials and writes the record
+        if (active && (pair % a.rsplit) == 0 && h == 0 && lane == 0) {
+            Peak m;
+            peak_init(m);
+            float pre = 0.f, pim = 0.f;
+            for (int w = 0; w < 2 * a.rsplit; ++w) {
+                const PairPartial pp = partial[warp + w];
+                Peak o;
+                o.mx = pp.mx;
+                o.idx = pp.idx;
+                o.cnt = pp.cnt;
+                o.sum = pp.sum;
+                peak_merge(m, o);
+                pre += pp.pr_re;
+                pim += pp.pr_im;
+            }
+            CellRecord rec;
+            rec.peak = m.mx;
+            rec.argmax = m.idx;
+            rec.sum = m.sum;
+            rec.count = m.cnt;
+            rec.probe_re = pre;
+            rec.probe_im = pim;
+            rec.pad_ = 0;
+            a.records[out] = rec;
+        }
+        __syncthreads();  // partial[] is free again
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// launch wrappers
+// ---------------------------------------------------------------------------------------------------------
+size_t spectra_smem_bytes(int s) { return (static_cast<size_t>(s) * kFft + kSpecWarps * kTileF2) * sizeof(float2); }
+size_t correlate_smem_bytes(int np) {
+    return (4 * static_cast<size_t>(kFft) + 2 * np * kTileF2) * sizeof(float2) + 2 * np * sizeof(PairPartial) + 16;
+}
+
+cudaError_t configure_kernels() {
+    cudaError_t e;
+    e = cudaFuncSetAttribute(k_doppler_spectra, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    const int s8 = static_cast<int>(correlate_smem_bytes(8)), s4 = static_cast<int>(correlate_smem_bytes(4));
+    e = cudaFuncSetAttribute(k_correlate_cells<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_correlate_cells<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_correlate_cells<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s4);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_correlate_cells<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s4);
+    return e;
+}
+
+cudaError_t launch_init_tables(float2* tw1, float2* tw2, cudaStream_t st) {
+    k_init_tables<<<4, 256, 0, st>>>(tw1, tw2);
+    return cudaGetLastError();
+}
+cudaError_t launch_replica_spectra(const uint8_t* chips_dev, int n_prn, float2* crep, cudaStream_t st) {
+    k_replica_spectra<<<dim3(kPad / 128, n_prn), 128, 0, st>>>(chips_dev, crep);
+    return cudaGetLastError();
+}
+cudaError_t launch_doppler_spectra(const SpectraArgs& a, cudaStream_t st) {
+    k_doppler_spectra<<<a.n_units * a.M, kSpecWarps * 32, spectra_smem_bytes(a.s), st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_correlate_cells(const CorrelateArgs& a, int np, int grid, cudaStream_t st) {
+    const size_t sm = correlate_smem_bytes(np);
+    if (np == 8) {
+        if (a.kind == kKindCoherent) k_correlate_cells<8, 1><<<grid, 512, sm, st>>>(a);
+        else k_correlate_cells<8, 2><<<grid, 512, sm, st>>>(a);
+    } else {
+        if (a.kind == kKindCoherent) k_correlate_cells<4, 1><<<grid, 256, sm, st>>>(a);
+        else k_correlate_cells<4, 2><<<grid, 256, sm, st>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace gb

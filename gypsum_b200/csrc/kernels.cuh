@@ -1,0 +1,53 @@
+// Kernel argument blocks and launch wrappers (implemented in kernels.cu, used by engine.cu).
+#pragma once
+#include "gb_common.cuh"
+
+namespace gb {
+
+constexpr int kKindCoherent = 1;     // utils.py:23-25: IntegrationType.Coherent = auto() -> 1
+constexpr int kKindNonCoherent = 2;  // IntegrationType.NonCoherent -> 2
+
+// doppler_spectra: one CTA per (unique Doppler u, millisecond i).
+struct SpectraArgs {
+    const float2* iq;        // complex64 samples, block b starts at b * block_stride
+    const double* doppler;   // [n_doppler] Hz
+    float2* spec;            // [n_blocks*n_doppler][M][s][2][1024]
+    const float2* tw1;       // [32][32]  exp(-2 pi i lane k1 / 1024)
+    const float2* tw2;       // [1024]    exp(-2 pi i n / 2048)
+    long long block_stride;  // samples between consecutive blocks (= M*N)
+    double inv_fs;
+    int N, s, M, n_doppler, n_units;  // n_units = n_blocks * n_doppler
+};
+
+// correlate_cells: one warp pair per (cell, r-range); NP pairs per CTA all on the same PRN.
+struct CorrelateArgs {
+    const float2* spec;
+    const float2* crep;  // [n_prn][2][1024]  conj(FFT2048(c'))/2048, even / odd bins
+    const float2* tw1;   // [32][32]
+    const float2* tw2;   // [1024]
+    CellRecord* records;
+    float* profile;      // optional: full profile of the single cell (N floats, or 2N when coherent)
+    int N, s, M, kind;
+    int rsplit;          // pairs cooperating on one cell (divides s and NP)
+    int n_groups;
+    // grid mode (cells = blocks x prn list x doppler list)
+    int grid_mode, P, D, chunks;  // chunks = ceil(D / cells_per_group)
+    const int* prn_idx;           // [P]
+    // list mode (cells sorted by PRN)
+    const int* grp_first;
+    const int* grp_count;
+    const int* grp_prn;
+    const int* cell_u;      // spectrum unit of each sorted cell
+    const int* cell_out;    // where its record goes
+    const int* cell_probe;  // coherent probe index or -1 (both modes, indexed by output slot; may be null)
+};
+
+size_t spectra_smem_bytes(int s);
+size_t correlate_smem_bytes(int np);
+cudaError_t launch_init_tables(float2* tw1, float2* tw2, cudaStream_t st);
+cudaError_t launch_replica_spectra(const uint8_t* chips_dev, int n_prn, float2* crep, cudaStream_t st);
+cudaError_t launch_doppler_spectra(const SpectraArgs& a, cudaStream_t st);
+cudaError_t launch_correlate_cells(const CorrelateArgs& a, int np, int grid, cudaStream_t st);
+cudaError_t configure_kernels();
+
+}  // namespace gb

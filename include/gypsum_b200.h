@@ -1,0 +1,98 @@
+/* gypsum_b200 -- C ABI of the B200 acquisition / tracking correlation engine.
+ *
+ * The reference (codyd51/gypsum) has no FFI: its boundary for this path is two Python classes and one pure
+ * function.  Each entry point below names the reference interface it stands behind (paths relative to the
+ * reference checkout).  Plain pointers and sizes only; the library owns every device allocation behind the
+ * handle; host arrays belong to the caller and are only read/written during the call.  All functions return 0
+ * on success or a GB200_E* code; gb200_last_error() gives the message.  There is no CPU fallback: without a
+ * CUDA device gb200_create fails.
+ *
+ * Threading: one caller thread per engine (the reference is single-threaded, receiver.py:85-146).  Host-pointer
+ * entry points return after the results are on the host; *_device entry points only enqueue work on the
+ * engine's stream (gb200_set_stream).
+ */
+#ifndef GYPSUM_B200_H
+#define GYPSUM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GB200_ABI_VERSION 1
+
+#define GB200_OK 0
+#define GB200_EINVAL 1  /* bad argument            -> ValueError  (utils.py:106) */
+#define GB200_ECUDA 2   /* CUDA runtime failure     -> RuntimeError */
+#define GB200_ESTATE 3  /* replicas / IQ not loaded -> RuntimeError (acquisition.py:112) */
+
+/* utils.py:23-25  IntegrationType(Enum): Coherent = auto() (1), NonCoherent = auto() (2) */
+#define GB200_COHERENT 1
+#define GB200_NON_COHERENT 2
+
+typedef struct gb200_engine gb200_engine;
+
+/* One reduced correlation profile (32 bytes).  Replaces the f64[N] profile that utils.py:77-108 returns and
+ * that acquisition.py:180-189 immediately reduces with np.max / np.argmax /
+ * get_normalized_correlation_peak_strength (utils.py:111-116):
+ *     strength = peak / ((sum - count*peak) / (N - count)).                                             */
+typedef struct gb200_cell_record {
+    float peak;      /* np.max(profile); for coherent integration, max |profile|                */
+    int32_t argmax;  /* np.argmax(profile): first index attaining the max, 0..N-1               */
+    double sum;      /* sum of all N profile values                                             */
+    int32_t count;   /* number of values equal to peak (utils.py:113 drops every one of them)   */
+    float probe_re;  /* coherent only: profile[probe_idx] (acquisition.py:136 np.angle input)    */
+    float probe_im;
+    int32_t reserved;
+} gb200_cell_record;
+
+int gb200_abi_version(void);
+
+/* receiver.py:46-66: one engine per stream format.  samples_per_ms must be a multiple of 1023
+ * (antenna_sample_provider.py:131-136, SampleProviderAttributes).                                  */
+int gb200_create(int device_ordinal, int samples_per_second, int samples_per_ms, gb200_engine** out);
+int gb200_destroy(gb200_engine* e);
+/* e may be NULL: message of the last failed gb200_create on this thread. */
+const char* gb200_last_error(const gb200_engine* e);
+
+/* Work is enqueued on this cudaStream_t (0 / NULL = the engine's own stream). */
+int gb200_set_stream(gb200_engine* e, void* cuda_stream);
+
+/* satellite.py:20-31 GpsSatellite.prn_as_complex + gps_ca_prn_codes.py:120-131: chips[n_prn][1023] in {0,1};
+ * replica index p in later calls refers to row p.  Builds conj(FFT(replica)) on the device once
+ * (the reference redoes np.fft.fft(prn_replica) on every call, utils.py:66).                        */
+int gb200_set_replicas(gb200_engine* e, const uint8_t* chips, int n_prn);
+
+/* receiver.py:219 antenna_data: complex64[n_samples] (interleaved float32 I,Q -- the on-disk format of
+ * antenna_sample_provider.py:112-119).  upload copies from the host; bind uses a device buffer in place.    */
+int gb200_upload_iq(gb200_engine* e, const float* iq_host, int64_t n_samples);
+int gb200_bind_iq_device(gb200_engine* e, const void* iq_device, int64_t n_samples);
+
+/* Benchmark-shaped search grid: the loaded IQ holds n_blocks independent blocks of
+ * ms_per_block milliseconds; every (block, prn_idx[a], doppler_hz[b]) cell is one
+ * utils.py:77 integrate_correlation_with_doppler_shifted_prn evaluation reduced to a record.
+ * out[(block*n_prn + a)*n_doppler + b].                                                             */
+int gb200_acquire_grid(gb200_engine* e, int n_blocks, int ms_per_block, const int32_t* prn_idx, int n_prn,
+                       const double* doppler_hz, int n_doppler, int integration_type, gb200_cell_record* out_host);
+int gb200_acquire_grid_device(gb200_engine* e, int n_blocks, int ms_per_block, const int32_t* prn_idx, int n_prn,
+                              const double* doppler_hz, int n_doppler, int integration_type, void* out_device);
+
+/* acquisition.py:154-190 get_best_doppler_shift_estimation / :122-136: an arbitrary list of (prn, Doppler)
+ * cells over the first n_ms milliseconds of the loaded IQ.  probe_idx (may be NULL) gives, per cell, the
+ * profile index whose complex value is wanted for coherent integration, or -1.                      */
+int gb200_acquire_cells(gb200_engine* e, int n_cells, const int32_t* prn_idx, const double* doppler_hz,
+                        const int32_t* probe_idx, int n_ms, int integration_type, gb200_cell_record* out_host);
+
+/* utils.py:77-108 in full: the N-value profile of one cell.  out_host holds N floats (non-coherent) or
+ * 2N floats (coherent, interleaved re,im).                                                          */
+int gb200_correlation_profile(gb200_engine* e, int prn_idx, double doppler_hz, int n_ms, int integration_type,
+                              float* out_host);
+
+/* Kernels launched by this engine so far (bench.py's gpu_launches). */
+int gb200_launch_count(const gb200_engine* e, int64_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GYPSUM_B200_H */

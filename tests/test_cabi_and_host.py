@@ -1,0 +1,73 @@
+"""CPU-side checks of the boundary: the shared library builds, loads and exports every symbol the header
+declares; host-side argument handling; replica recognition.  No compute calls (no GPU here)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import gypsum_oracle as o
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(native_lib):
+    from gypsum_b200 import _native
+
+    header = open(os.path.join(ROOT, "include", "gypsum_b200.h")).read()
+    declared = set(re.findall(r"\b(gb200_[a-z_]+)\s*\(", header))
+    assert declared == set(_native.SYMBOLS), declared ^ set(_native.SYMBOLS)
+    for name in declared:
+        assert getattr(native_lib, name) is not None
+    assert native_lib.gb200_abi_version() == 1
+    assert _native.RECORD_DTYPE.itemsize == 32
+    assert [_native.RECORD_DTYPE.fields[k][1] for k in ("peak", "argmax", "sum", "count", "probe_re", "probe_im")] == [
+        0, 4, 8, 16, 20, 24]
+
+
+def test_no_gpu_is_an_error_not_a_fallback(native_lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from gypsum_b200 import _native
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _native.Engine(2046000, 2046)
+    with pytest.raises(ValueError):
+        _native.Engine(2046000, 2047)  # not a multiple of 1023
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "gypsum_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("the oracle", ""), f"{f} mentions oracle"
+                assert "/root/reference" not in text
+
+
+def test_replica_recognition():
+    from gypsum_b200.utils import chips_of_replica
+
+    for n in (2046, 4092):
+        prn = o.replica(5, n)
+        chips, roll = chips_of_replica(prn, n)
+        assert roll == 0 and np.array_equal(chips, o.ca_code(5).astype(np.uint8))
+        s = n // 1023
+        for shift in (1, s, 777, n - 1):
+            c2, r2 = chips_of_replica(np.roll(prn, shift), n)
+            assert np.array_equal(np.roll(np.repeat(2.0 * c2 - 1, s), r2), np.roll(prn, shift).real)
+    with pytest.raises(ValueError):
+        chips_of_replica(np.ones(2046) * 0.5, 2046)
+    with pytest.raises(ValueError):
+        chips_of_replica(o.replica(5, 2046)[:-1], 2046)
+
+
+def test_integration_type_enum_matches_reference_values():
+    from gypsum_b200.utils import IntegrationType, _kind
+
+    assert IntegrationType.Coherent.value == 1 and IntegrationType.NonCoherent.value == 2
+    assert _kind(IntegrationType.Coherent) == 1 and _kind(IntegrationType.NonCoherent) == 2
+    with pytest.raises(ValueError, match="Unexpected integration type"):
+        _kind("nope")

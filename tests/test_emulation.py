@@ -1,0 +1,38 @@
+"""The product's lane-level device functions (warp FFT-1024, polyphase split, padded-FFT correlation, replica
+spectra) executed on the CPU by the lane emulator and compared with the oracle.  No GPU needed."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import gypsum_oracle as o
+
+
+@pytest.mark.parametrize("inverse", [0, 1])
+def test_warp_fft1024(emu_lib, inverse):
+    rng = np.random.default_rng(inverse)
+    x = (rng.standard_normal(1024) + 1j * rng.standard_normal(1024)).astype(np.complex64)
+    y = x.copy()
+    emu_lib.emu_fft1024(y.ctypes.data_as(ctypes.c_void_p), inverse)
+    ref = np.fft.ifft(x.astype(complex)) * 1024 if inverse else np.fft.fft(x.astype(complex))
+    assert np.abs(y - ref).max() <= 5e-7 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("n,n_ms,sv,f", [(2046, 1, 25, 1500.0), (2046, 3, 7, -3250.0), (4092, 2, 11, 4875.5),
+                                         (16368, 1, 32, -250.0), (1023, 2, 1, 700.0), (3069, 1, 19, 10000.0)])
+def test_polyphase_correlation_matches_oracle(emu_lib, n, n_ms, sv, f):
+    emu_lib.emu_cell_profile.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                         ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    fs = n * 1000
+    iq = o.synth_iq(1, n, n_ms, fs, [(sv, f + 3, n - 7, 0.3, 0.3)])
+    chips = o.ca_code(sv).astype(np.uint8)
+    prn = o.replica(sv, n)
+    nc = np.zeros(n, np.float32)
+    emu_lib.emu_cell_profile(iq.ctypes.data, n, n_ms, float(fs), float(f), chips.ctypes.data, 2, nc.ctypes.data)
+    ref = o.integrate(o.NON_COHERENT, iq, fs, n, f, prn)
+    assert np.abs(nc - ref).max() <= 1e-6 * ref.max()
+    assert nc.argmax() == ref.argmax() == n - 7
+    co = np.zeros(n, np.complex64)
+    emu_lib.emu_cell_profile(iq.ctypes.data, n, n_ms, float(fs), float(f), chips.ctypes.data, 1, co.ctypes.data)
+    refc = o.integrate(o.COHERENT, iq, fs, n, f, prn)
+    assert np.abs(co - refc).max() <= 1e-6 * np.abs(refc).max()
