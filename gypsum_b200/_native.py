@@ -35,6 +35,8 @@ SYMBOLS = {
     "gb200_acquire_cells": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P]),
     "gb200_correlation_profile": (C.c_int, [_P, C.c_int, C.c_double, C.c_int, C.c_int, _P]),
     "gb200_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "gb200_enable_kernel_timing": (C.c_int, [_P, C.c_int]),
+    "gb200_kernel_timing": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
 
 _lib = None
@@ -108,6 +110,15 @@ class Engine:
         n = C.c_int64()
         self._check(self._lib.gb200_launch_count(self._h, C.byref(n)), "gb200_launch_count")
         return n.value
+
+    def enable_kernel_timing(self, on: bool) -> None:
+        self._check(self._lib.gb200_enable_kernel_timing(self._h, int(bool(on))), "gb200_enable_kernel_timing")
+
+    def kernel_timing(self, which: int) -> tuple[float, int]:
+        """(total device ms, launches) of doppler_spectra (0) / correlate_cells (1) since timing was enabled."""
+        ms, n = C.c_double(), C.c_int64()
+        self._check(self._lib.gb200_kernel_timing(self._h, which, C.byref(ms), C.byref(n)), "gb200_kernel_timing")
+        return ms.value, n.value
 
     # -- inputs --------------------------------------------------------------------------------------------
     def set_replicas(self, chips: np.ndarray) -> None:

@@ -92,6 +92,9 @@ struct gb200_engine {
     int64_t launches = 0;
     size_t spec_budget_bytes = 80u << 20;
     int np = 8, rsplit_override = 0;
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[2];
+    size_t ev_used[2] = {0, 0};
     std::string err;
 };
 
@@ -114,10 +117,35 @@ struct gb200_engine {
 
 namespace {
 
+// optional event bracket around one kernel launch (measurement aid, off by default)
+struct TimedLaunch {
+    gb200_engine* e;
+    int which;
+    cudaEvent_t stop = nullptr;
+    TimedLaunch(gb200_engine* e_, int which_) : e(e_), which(which_) {
+        if (!e->timing) return;
+        auto& pool = e->ev[which];
+        if (e->ev_used[which] == pool.size()) {
+            cudaEvent_t a, b;
+            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+            pool.emplace_back(a, b);
+        }
+        auto& pr = pool[e->ev_used[which]++];
+        cudaEventRecord(pr.first, e->stream);
+        stop = pr.second;
+    }
+    ~TimedLaunch() {
+        if (stop) cudaEventRecord(stop, e->stream);
+    }
+};
+
 int gcd_int(int a, int b) { return b ? gcd_int(b, a % b) : a; }
 
-int pick_rsplit(const gb200_engine* e) {
+// How many warp pairs share one cell.  With plenty of cells per pair each pair keeps a whole cell (no cross-pair
+// merge, no CTA-wide barrier); small launches split a cell's polyphase branches over pairs to fill the machine.
+int pick_rsplit(const gb200_engine* e, long long n_cells) {
     if (e->rsplit_override > 0 && e->s % e->rsplit_override == 0 && e->np % e->rsplit_override == 0) return e->rsplit_override;
+    if (n_cells >= 8LL * e->num_sms * e->np) return 1;
     return gcd_int(e->s, e->np);
 }
 
@@ -170,7 +198,7 @@ int run_grid(gb200_engine* e, int n_blocks, int M, const int32_t* prn_idx, int P
     nb = std::min(nb, n_blocks);
     GB_CUDA(e, e->spec.ensure(per_block * nb));
 
-    const int rsplit = pick_rsplit(e);
+    const int rsplit = pick_rsplit(e, static_cast<long long>(nb) * P * D);
     const int cpg = e->np / rsplit;
     const int chunks = (D + cpg - 1) / cpg;
     for (int b0 = 0; b0 < n_blocks; b0 += nb) {
@@ -188,7 +216,10 @@ int run_grid(gb200_engine* e, int n_blocks, int M, const int32_t* prn_idx, int P
         sa.M = M;
         sa.n_doppler = D;
         sa.n_units = nbb * D;
-        GB_CUDA(e, launch_doppler_spectra(sa, e->stream));
+        {
+            TimedLaunch tl(e, 0);
+            GB_CUDA(e, launch_doppler_spectra(sa, e->stream));
+        }
         e->launches++;
 
         CorrelateArgs ca{};
@@ -210,8 +241,11 @@ int run_grid(gb200_engine* e, int n_blocks, int M, const int32_t* prn_idx, int P
         ca.chunks = chunks;
         ca.prn_idx = e->d_ints.p;
         ca.cell_probe = nullptr;
-        const int grid = std::min(ca.n_groups, e->num_sms * (e->np == 8 ? 1 : 2));
-        GB_CUDA(e, launch_correlate_cells(ca, e->np, grid, e->stream));
+        const int grid = std::min(ca.n_groups, e->num_sms);
+        {
+            TimedLaunch tl(e, 1);
+            GB_CUDA(e, launch_correlate_cells(ca, e->np, grid, e->stream));
+        }
         e->launches++;
     }
     return GB200_OK;
@@ -230,7 +264,7 @@ int run_cells(gb200_engine* e, int n_cells, const int32_t* prn_idx, const double
         if (prn_idx[i] < 0 || prn_idx[i] >= e->n_prn) GB_FAIL(e, GB200_EINVAL, "prn index %d out of range", prn_idx[i]);
     e->grid_cache_valid = false;  // d_ints / d_doppler are about to be overwritten
 
-    const int rsplit = pick_rsplit(e);
+    const int rsplit = pick_rsplit(e, n_cells);
     const int cpg = e->np / rsplit;
     std::vector<int> order(n_cells);
     std::iota(order.begin(), order.end(), 0);
@@ -306,7 +340,10 @@ int run_cells(gb200_engine* e, int n_cells, const int32_t* prn_idx, const double
         sa.M = M;
         sa.n_doppler = nu;
         sa.n_units = nu;
-        GB_CUDA(e, launch_doppler_spectra(sa, e->stream));
+        {
+            TimedLaunch tl(e, 0);
+            GB_CUDA(e, launch_doppler_spectra(sa, e->stream));
+        }
         e->launches++;
 
         CorrelateArgs ca{};
@@ -329,8 +366,11 @@ int run_cells(gb200_engine* e, int n_cells, const int32_t* prn_idx, const double
         ca.grp_count = di + 2 * nc + ng;
         ca.grp_prn = di + 2 * nc + 2 * ng;
         ca.cell_probe = e->d_ints.p;
-        const int grid = std::min(ng, e->num_sms * (e->np == 8 ? 1 : 2));
-        GB_CUDA(e, launch_correlate_cells(ca, e->np, grid, e->stream));
+        const int grid = std::min(ng, e->num_sms);
+        {
+            TimedLaunch tl(e, 1);
+            GB_CUDA(e, launch_correlate_cells(ca, e->np, grid, e->stream));
+        }
         e->launches++;
         c0 = c1;
     }
@@ -374,7 +414,7 @@ int gb200_create(int device, int fs, int n, gb200_engine** out) {
     e->N = n;
     e->s = n / kChips;
     e->spec_budget_bytes = static_cast<size_t>(env_int("GB200_SPEC_BUDGET_MB", 80)) << 20;
-    e->np = env_int("GB200_NP", 8) == 4 ? 4 : 8;
+    e->np = 8;
     e->rsplit_override = env_int("GB200_RSPLIT", 0);
     auto fail = [&](cudaError_t c, const char* what) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(c);
@@ -427,6 +467,11 @@ int gb200_destroy(gb200_engine* e) {
     e->h_ints.release();
     e->h_doubles.release();
     e->h_profile.release();
+    for (auto& pool : e->ev)
+        for (auto& pr : pool) {
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
     return GB200_OK;
@@ -535,6 +580,30 @@ int gb200_correlation_profile(gb200_engine* e, int prn, double dop, int n_ms, in
     GB_CUDA(e, cudaMemcpyAsync(e->h_profile.p, e->d_profile.p, nf * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     GB_CUDA(e, cudaStreamSynchronize(e->stream));
     memcpy(out_host, e->h_profile.p, nf * sizeof(float));
+    return GB200_OK;
+}
+
+int gb200_enable_kernel_timing(gb200_engine* e, int on) {
+    if (!e) return GB200_EINVAL;
+    GB_CUDA(e, cudaSetDevice(e->device));
+    GB_CUDA(e, cudaStreamSynchronize(e->stream));
+    e->timing = on != 0;
+    e->ev_used[0] = e->ev_used[1] = 0;
+    return GB200_OK;
+}
+
+int gb200_kernel_timing(gb200_engine* e, int which, double* total_ms, int64_t* launches) {
+    if (!e || which < 0 || which > 1 || !total_ms || !launches) return GB200_EINVAL;
+    GB_CUDA(e, cudaSetDevice(e->device));
+    GB_CUDA(e, cudaStreamSynchronize(e->stream));
+    double t = 0.0;
+    for (size_t i = 0; i < e->ev_used[which]; ++i) {
+        float ms = 0.f;
+        GB_CUDA(e, cudaEventElapsedTime(&ms, e->ev[which][i].first, e->ev[which][i].second));
+        t += ms;
+    }
+    *total_ms = t;
+    *launches = static_cast<int64_t>(e->ev_used[which]);
     return GB200_OK;
 }
 

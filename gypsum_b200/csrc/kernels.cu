@@ -142,26 +142,27 @@ struct PairPartial {  // exchanged through shared memory when several pairs shar
     int pad;
 };
 
+// Warp-level merge of per-thread peaks: REDUX for (max, first index, count), shuffles for the float64 sum.
+// Profile values are >= 0 (an excluded slot holds -1), so their IEEE bit patterns order like signed ints.
 __device__ __forceinline__ void warp_reduce_peak(Peak& p) {
+    const int bits = __float_as_int(p.mx);
+    const int mb = __reduce_max_sync(0xffffffffu, bits);
+    const bool is = bits == mb;
+    p.idx = __reduce_min_sync(0xffffffffu, is ? p.idx : 0x7fffffff);
+    p.cnt = __reduce_add_sync(0xffffffffu, is ? p.cnt : 0);
+    p.mx = __int_as_float(mb);
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        Peak o;
-        o.mx = __shfl_xor_sync(0xffffffffu, p.mx, off);
-        o.idx = __shfl_xor_sync(0xffffffffu, p.idx, off);
-        o.cnt = __shfl_xor_sync(0xffffffffu, p.cnt, off);
-        o.sum = __shfl_xor_sync(0xffffffffu, p.sum, off);
-        peak_merge(p, o);
-    }
+    for (int off = 16; off > 0; off >>= 1) p.sum += __shfl_xor_sync(0xffffffffu, p.sum, off);
 }
 
-template <int NP, int KIND>
+template <int NP, int KIND, bool PROFILE>
 __global__ void __launch_bounds__(NP * 64, (NP == 8 ? 1 : 2)) k_correlate_cells(const CorrelateArgs a) {
     extern __shared__ __align__(16) float2 smem[];
     float2* crep_s = smem;                 // [2][1024]
     float2* tw1_s = crep_s + 2 * kFft;     // [32][32]
     float2* tw2_s = tw1_s + kFft;          // [1024]
     float2* tiles = tw2_s + kFft;          // [2*NP][kTileF2]
-    PairPartial* partial = reinterpret_cast<PairPartial*>(tiles + 2 * NP * kTileF2);  // [NP][2]
+    PairPartial* partial = reinterpret_cast<PairPartial*>(tiles + 2 * NP * kTileF2);  // [2*NP]
     uint64_t* mbar = reinterpret_cast<uint64_t*>(partial + 2 * NP);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -182,23 +183,40 @@ __global__ void __launch_bounds__(NP * 64, (NP == 8 ? 1 : 2)) k_correlate_cells(
 
     const int cells_per_group = NP / a.rsplit;
     const int r_per_pair = a.s / a.rsplit;
-    const int my_cell = pair / a.rsplit;          // cell slot inside the group
+    const int my_cell = pair / a.rsplit;  // cell slot inside the group
     const int my_r0 = (pair % a.rsplit) * r_per_pair;
     const size_t unit_stride = static_cast<size_t>(a.M) * a.s * 2 * kFft;
     int cur_prn = -1;
 
-    for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x) {
+    // Each CTA walks a contiguous range of groups: consecutive groups share the PRN, so the replica spectrum is
+    // re-staged only when the PRN changes, and the (block, prn, chunk) decode is incremental.
+    const int g0 = static_cast<int>(static_cast<long long>(blockIdx.x) * a.n_groups / gridDim.x);
+    const int g1 = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * a.n_groups / gridDim.x);
+    int gb = 0, gpl = 0, gch = 0;
+    if (a.grid_mode && g0 < g1) {
+        const int per_block = a.P * a.chunks;
+        gb = g0 / per_block;
+        const int rem = g0 - gb * per_block;
+        gpl = rem / a.chunks;
+        gch = rem - gpl * a.chunks;
+    }
+
+    for (int g = g0; g < g1; ++g) {
         // ---- decode the group (uniform across the CTA) ----
         int prn, n_cells, unit = 0, out = 0;
         if (a.grid_mode) {
-            const int per_block = a.P * a.chunks;
-            const int b = g / per_block, rem = g % per_block;
-            const int pl = rem / a.chunks, ch = rem % a.chunks;
-            prn = a.prn_idx[pl];
-            n_cells = min(cells_per_group, a.D - ch * cells_per_group);
-            const int d = ch * cells_per_group + my_cell;
-            unit = b * a.D + d;
-            out = (b * a.P + pl) * a.D + d;
+            prn = a.prn_idx[gpl];
+            n_cells = min(cells_per_group, a.D - gch * cells_per_group);
+            const int d = gch * cells_per_group + my_cell;
+            unit = gb * a.D + d;
+            out = (gb * a.P + gpl) * a.D + d;
+            if (++gch == a.chunks) {
+                gch = 0;
+                if (++gpl == a.P) {
+                    gpl = 0;
+                    ++gb;
+                }
+            }
         } else {
             prn = a.grp_prn[g];
             n_cells = a.grp_count[g];
@@ -222,14 +240,14 @@ __global__ void __launch_bounds__(NP * 64, (NP == 8 ? 1 : 2)) k_correlate_cells(
             cur_prn = prn;
         }
 
-        Peak pk;
-        peak_init(pk);
-        float pr_re = 0.f, pr_im = 0.f;
         if (active) {
-            const int probe = (KIND == kKindCoherent && a.cell_probe) ? a.cell_probe[out] : -1;
+            Peak pk;
+            peak_init(pk);
+            float pr_re = 0.f, pr_im = 0.f;
+            int probe = -1;
+            if (KIND == kKindCoherent && a.cell_probe) probe = a.cell_probe[out];
             const float2* __restrict__ spec_u = a.spec + static_cast<size_t>(unit) * unit_stride;
             const float2* crep_h = crep_s + h * kFft;
-            float* prof = a.profile;
             for (int r = my_r0; r < my_r0 + r_per_pair; ++r) {
                 float acc[16];
 #pragma unroll
@@ -271,76 +289,54 @@ __global__ void __launch_bounds__(NP * 64, (NP == 8 ? 1 : 2)) k_correlate_cells(
                     __syncwarp();
                     wfft_phase2(im, re, lane, tile);
                     __syncwarp();
-                    if (h) mul_tw2_conj(re, im, lane, tw2_s);
-                    // out[k] = E[k] + W2048^-k O[k]: the even-bin warp finishes lags [0,512), the odd-bin
-                    // warp lags [512,1024); each hands the other half over through its (now idle) tile.
-                    if (h == 0) {
-#pragma unroll
-                        for (int jj = 0; jj < 16; ++jj) tile[jj * 32 + lane] = make_float2(re[16 + jj], im[16 + jj]);
-                    } else {
-#pragma unroll
-                        for (int jj = 0; jj < 16; ++jj) tile[jj * 32 + lane] = make_float2(re[jj], im[jj]);
-                    }
+                    exchange_store(re, im, lane, h, tile);
                     pair_barrier(pair);
                     float xr[16], xi[16];
-                    if (h == 0) {
-#pragma unroll
-                        for (int jj = 0; jj < 16; ++jj) {
-                            const float2 o = ptile[jj * 32 + lane];
-                            xr[jj] = re[jj] + o.x;
-                            xi[jj] = im[jj] + o.y;
-                        }
-                    } else {
-#pragma unroll
-                        for (int jj = 0; jj < 16; ++jj) {
-                            const float2 o = ptile[jj * 32 + lane];
-                            xr[jj] = re[16 + jj] + o.x;
-                            xi[jj] = im[16 + jj] + o.y;
-                        }
-                    }
+                    if (h == 0) combine_even(re, im, lane, tw2_s, ptile, xr, xi);
+                    else combine_odd(re, im, lane, tw2_s, ptile, xr, xi);
                     if (KIND == kKindCoherent) {
 #pragma unroll
                         for (int jj = 0; jj < 16; ++jj) {
-                            acc[jj] = sqrtf(xr[jj] * xr[jj] + xi[jj] * xi[jj]);
+                            acc[jj] = gb_sqrt(xr[jj] * xr[jj] + xi[jj] * xi[jj]);
                             const int q = lane + 32 * (16 * h + jj);
                             const int n = a.s * q + r;
-                            if (q < kChips) {
-                                if (n == probe) {
-                                    pr_re = xr[jj];
-                                    pr_im = xi[jj];
-                                }
-                                if (prof) {
-                                    prof[2 * n] = xr[jj];
-                                    prof[2 * n + 1] = xi[jj];
+                            if (n == probe && q < kChips) {
+                                pr_re = xr[jj];
+                                pr_im = xi[jj];
+                            }
+                            if (PROFILE) {
+                                if (q < kChips) {
+                                    a.profile[2 * n] = xr[jj];
+                                    a.profile[2 * n + 1] = xi[jj];
                                 }
                             }
                         }
                     } else {
 #pragma unroll
-                        for (int jj = 0; jj < 16; ++jj) acc[jj] += sqrtf(xr[jj] * xr[jj] + xi[jj] * xi[jj]);
+                        for (int jj = 0; jj < 16; ++jj) acc[jj] += gb_sqrt(xr[jj] * xr[jj] + xi[jj] * xi[jj]);
                     }
                     pair_barrier(pair);  // partner has read my tile; the next phase 1 may overwrite it
                 }
-                float psum = 0.f;
+                Peak t;
+                float fsum;
+                thread_peak16(acc, lane, h, a.s, r, t, fsum);
+                t.sum = static_cast<double>(fsum);
+                peak_merge(pk, t);
+                if (PROFILE && KIND != kKindCoherent) {
 #pragma unroll
-                for (int jj = 0; jj < 16; ++jj) {
-                    const int q = lane + 32 * (16 * h + jj);
-                    if (q < kChips) {
-                        const int n = a.s * q + r;
-                        peak_push(pk, acc[jj], n);
-                        psum += acc[jj];
-                        if (prof && KIND != kKindCoherent) prof[n] = acc[jj];
+                    for (int jj = 0; jj < 16; ++jj) {
+                        const int q = lane + 32 * (16 * h + jj);
+                        if (q < kChips) a.profile[a.s * q + r] = acc[jj];
                     }
                 }
-                pk.sum += static_cast<double>(psum);
             }
             warp_reduce_peak(pk);
-            pr_re += __shfl_xor_sync(0xffffffffu, pr_re, 16);
-            pr_im += __shfl_xor_sync(0xffffffffu, pr_im, 16);
+            if (KIND == kKindCoherent) {
 #pragma unroll
-            for (int off = 8; off > 0; off >>= 1) {
-                pr_re += __shfl_xor_sync(0xffffffffu, pr_re, off);
-                pr_im += __shfl_xor_sync(0xffffffffu, pr_im, off);
+                for (int off = 16; off > 0; off >>= 1) {
+                    pr_re += __shfl_xor_sync(0xffffffffu, pr_re, off);
+                    pr_im += __shfl_xor_sync(0xffffffffu, pr_im, off);
+                }
             }
             if (lane == 0) {
                 PairPartial pp;
@@ -354,8 +350,12 @@ __global__ void __launch_bounds__(NP * 64, (NP == 8 ? 1 : 2)) k_correlate_cells(
                 partial[warp] = pp;
             }
         }
-        __syncthreads();
-        // first warp of each cell merges the 2*rsplit partials and writes the record
+        // ---- merge the 2*rsplit warp partials of each cell and write its record ----
+        if (a.rsplit == 1) {
+            if (active) pair_barrier(pair);
+        } else {
+            __syncthreads();
+        }
         if (active && (pair % a.rsplit) == 0 && h == 0 && lane == 0) {
             Peak m;
             peak_init(m);
@@ -381,7 +381,8 @@ __global__ void __launch_bounds__(NP * 64, (NP == 8 ? 1 : 2)) k_correlate_cells(
             rec.pad_ = 0;
             a.records[out] = rec;
         }
-        __syncthreads();  // partial[] is free again
+        if (a.rsplit != 1) __syncthreads();  // partial[] is free again
+        // rsplit == 1: the next write to partial[] comes after at least two more pair barriers
     }
 }
 
@@ -397,14 +398,14 @@ cudaError_t configure_kernels() {
     cudaError_t e;
     e = cudaFuncSetAttribute(k_doppler_spectra, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    const int s8 = static_cast<int>(correlate_smem_bytes(8)), s4 = static_cast<int>(correlate_smem_bytes(4));
-    e = cudaFuncSetAttribute(k_correlate_cells<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8);
+    const int s8 = static_cast<int>(correlate_smem_bytes(8));
+    e = cudaFuncSetAttribute(k_correlate_cells<8, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_correlate_cells<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8);
+    e = cudaFuncSetAttribute(k_correlate_cells<8, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_correlate_cells<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s4);
+    e = cudaFuncSetAttribute(k_correlate_cells<8, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_correlate_cells<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s4);
+    e = cudaFuncSetAttribute(k_correlate_cells<8, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8);
     return e;
 }
 
@@ -421,13 +422,15 @@ cudaError_t launch_doppler_spectra(const SpectraArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 cudaError_t launch_correlate_cells(const CorrelateArgs& a, int np, int grid, cudaStream_t st) {
-    const size_t sm = correlate_smem_bytes(np);
-    if (np == 8) {
-        if (a.kind == kKindCoherent) k_correlate_cells<8, 1><<<grid, 512, sm, st>>>(a);
-        else k_correlate_cells<8, 2><<<grid, 512, sm, st>>>(a);
+    (void)np;  // one build: 8 warp pairs per CTA, one CTA per SM
+    const size_t sm = correlate_smem_bytes(8);
+    const bool prof = a.profile != nullptr;
+    if (a.kind == kKindCoherent) {
+        if (prof) k_correlate_cells<8, 1, true><<<grid, 512, sm, st>>>(a);
+        else k_correlate_cells<8, 1, false><<<grid, 512, sm, st>>>(a);
     } else {
-        if (a.kind == kKindCoherent) k_correlate_cells<4, 1><<<grid, 256, sm, st>>>(a);
-        else k_correlate_cells<4, 2><<<grid, 256, sm, st>>>(a);
+        if (prof) k_correlate_cells<8, 2, true><<<grid, 512, sm, st>>>(a);
+        else k_correlate_cells<8, 2, false><<<grid, 512, sm, st>>>(a);
     }
     return cudaGetLastError();
 }

@@ -94,6 +94,85 @@ GB_HD GB_INLINE void mul_tw2(float (&re)[32], float (&im)[32], int lane, const f
         im[j] = a * w.y + b * w.x;
     }
 }
+// Fast magnitude: MUFU.SQRT (sqrt.approx, ~1 ulp) on the device instead of the IEEE sequence with its slow path.
+GB_HD GB_INLINE float gb_sqrt(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return __builtin_sqrtf(x);
+#endif
+}
+
+// Radix-2 recombination of the two inverse half transforms, out[k] = E[k] + conj(W2048^k) O[k], split so both
+// warps of a pair do the same amount of work: the even-bin warp finishes lags k = lane + 32 jj (jj < 16) from
+// its own E and the partner's raw O; the odd-bin warp finishes k = lane + 32 (16 + jj) from its own O and the
+// partner's E.  `theirs` is the partner's exchange tile ([jj*32 + lane]).
+GB_HD GB_INLINE void combine_even(const float (&re)[32], const float (&im)[32], int lane, const float2* tw2,
+                                  const float2* theirs, float (&xr)[16], float (&xi)[16]) {
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) {
+        const float2 o = theirs[jj * 32 + lane];
+        const float2 w = tw2[lane + 32 * jj];
+        xr[jj] = re[jj] + (o.x * w.x + o.y * w.y);
+        xi[jj] = im[jj] + (o.y * w.x - o.x * w.y);
+    }
+}
+GB_HD GB_INLINE void combine_odd(const float (&re)[32], const float (&im)[32], int lane, const float2* tw2,
+                                 const float2* theirs, float (&xr)[16], float (&xi)[16]) {
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) {
+        const float2 e = theirs[jj * 32 + lane];
+        const float2 w = tw2[lane + 32 * (16 + jj)];
+        xr[jj] = e.x + (re[16 + jj] * w.x + im[16 + jj] * w.y);
+        xi[jj] = e.y + (im[16 + jj] * w.x - re[16 + jj] * w.y);
+    }
+}
+// What each warp hands to its partner: the even-bin warp its E[k] for the upper lags, the odd-bin warp its raw
+// O[k] for the lower lags.
+GB_HD GB_INLINE void exchange_store(const float (&re)[32], const float (&im)[32], int lane, int h, float2* mine) {
+    if (h == 0) {
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) mine[jj * 32 + lane] = make_float2(re[16 + jj], im[16 + jj]);
+    } else {
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) mine[jj * 32 + lane] = make_float2(re[jj], im[jj]);
+    }
+}
+
+// Branch-free reduction of one thread's 16 finished lags (q = lane + 32 (16 h + jj), profile index s q + r) into
+// (max, first index of max, count of max, sum).  Lag 1023 does not exist (only lane 31, h = 1, jj = 15).
+GB_HD GB_INLINE void thread_peak16(const float (&v)[16], int lane, int h, int s, int r, Peak& out, float& fsum) {
+    const bool last_invalid = (h == 1) && (lane == 31);
+    float m = v[0];
+    float sm = v[0];
+#pragma unroll
+    for (int jj = 1; jj < 15; ++jj) {
+        m = m > v[jj] ? m : v[jj];
+        sm += v[jj];
+    }
+    const float v15 = last_invalid ? -1.0f : v[15];
+    m = m > v15 ? m : v15;
+    sm += last_invalid ? 0.0f : v[15];
+    int first = 15, c = 0;
+    {
+        const bool eq = v15 == m;
+        c += eq ? 1 : 0;
+    }
+#pragma unroll
+    for (int jj = 14; jj >= 0; --jj) {
+        const bool eq = v[jj] == m;
+        first = eq ? jj : first;
+        c += eq ? 1 : 0;
+    }
+    out.mx = m;
+    out.idx = s * (lane + 32 * (16 * h + first)) + r;
+    out.cnt = c;
+    out.sum = 0.0;
+    fsum = sm;
+}
+
 GB_HD GB_INLINE void mul_tw2_conj(float (&re)[32], float (&im)[32], int lane, const float2* tw2) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) {

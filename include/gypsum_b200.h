@@ -92,6 +92,12 @@ int gb200_correlation_profile(gb200_engine* e, int prn_idx, double doppler_hz, i
 /* Kernels launched by this engine so far (bench.py's gpu_launches). */
 int gb200_launch_count(const gb200_engine* e, int64_t* out);
 
+/* Measurement aid (bench.py roofline): when enabled, every doppler_spectra (which = 0) / correlate_cells
+ * (which = 1) launch is bracketed by CUDA events on the engine's stream; gb200_kernel_timing synchronises and
+ * returns the summed device time and the number of launches since timing was enabled.                 */
+int gb200_enable_kernel_timing(gb200_engine* e, int on);
+int gb200_kernel_timing(gb200_engine* e, int which, double* total_ms, int64_t* launches);
+
 #ifdef __cplusplus
 }
 #endif

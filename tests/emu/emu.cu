@@ -73,7 +73,7 @@ void emu_replica_spectrum(const uint8_t* chips, float2* crep) {
 // Full per-cell pipeline.  iq: complex64[n_ms*N]; out: float[N] (non-coherent) or float2[N] (coherent).
 // kind: 1 coherent, 2 non-coherent (utils.py:23-25).
 void emu_cell_profile(const float2* iq, int N, int n_ms, double fs, double doppler, const uint8_t* chips, int kind,
-                      float* out) {
+                      float* out, CellRecord* rec_out) {
     init_tables();
     const int s = N / kChips;
     std::vector<float2> crep(2048);
@@ -108,7 +108,11 @@ void emu_cell_profile(const float2* iq, int N, int n_ms, double fs, double doppl
     if (kind == 2) memset(out, 0, sizeof(float) * N);
     else memset(out, 0, sizeof(float) * 2 * N);
     const int n_iter = kind == 1 ? 1 : n_ms;
+    Peak cell;
+    peak_init(cell);
+    std::vector<float> acc((size_t)2 * 32 * 16);  // [h][lane][jj]
     for (int r = 0; r < s; ++r) {
+        std::fill(acc.begin(), acc.end(), 0.f);
         for (int it = 0; it < n_iter; ++it) {
             for (int half = 0; half < 2; ++half) {
                 WarpRegs* ww = half ? wo : w;
@@ -129,22 +133,52 @@ void emu_cell_profile(const float2* iq, int N, int n_ms, double fs, double doppl
                         ww->im[lane][j] = y.y;
                     }
                 warp_fft1024(*ww, true, half ? tileO.data() : tile.data());
-                if (half)
-                    for (int lane = 0; lane < 32; ++lane) mul_tw2_conj(ww->re[lane], ww->im[lane], lane, g_tw2.data());
+                // (all lanes have finished phase 2 before the tile is reused for the exchange)
+                for (int lane = 0; lane < 32; ++lane)
+                    exchange_store(ww->re[lane], ww->im[lane], lane, half, half ? tileO.data() : tile.data());
             }
-            for (int lane = 0; lane < 32; ++lane)
-                for (int j = 0; j < 32; ++j) {
-                    const int q = lane + 32 * j;
-                    if (q >= kChips) continue;
-                    const float xr = w->re[lane][j] + wo->re[lane][j], xi = w->im[lane][j] + wo->im[lane][j];
-                    const int n = s * q + r;
-                    if (kind == 2) out[n] += sqrtf(xr * xr + xi * xi);
-                    else {
-                        out[2 * n] = xr;
-                        out[2 * n + 1] = xi;
+            for (int half = 0; half < 2; ++half)
+                for (int lane = 0; lane < 32; ++lane) {
+                    float xr[16], xi[16];
+                    if (half == 0) combine_even(w->re[lane], w->im[lane], lane, g_tw2.data(), tileO.data(), xr, xi);
+                    else combine_odd(wo->re[lane], wo->im[lane], lane, g_tw2.data(), tile.data(), xr, xi);
+                    for (int jj = 0; jj < 16; ++jj) {
+                        const int q = lane + 32 * (16 * half + jj);
+                        const int n = s * q + r;
+                        float& a = acc[((size_t)half * 32 + lane) * 16 + jj];
+                        if (kind == 2) a += gb_sqrt(xr[jj] * xr[jj] + xi[jj] * xi[jj]);
+                        else {
+                            a = gb_sqrt(xr[jj] * xr[jj] + xi[jj] * xi[jj]);
+                            if (q < kChips) {
+                                out[2 * n] = xr[jj];
+                                out[2 * n + 1] = xi[jj];
+                            }
+                        }
                     }
                 }
         }
+        for (int half = 0; half < 2; ++half)
+            for (int lane = 0; lane < 32; ++lane) {
+                float v[16];
+                for (int jj = 0; jj < 16; ++jj) {
+                    v[jj] = acc[((size_t)half * 32 + lane) * 16 + jj];
+                    const int q = lane + 32 * (16 * half + jj);
+                    if (kind == 2 && q < kChips) out[s * q + r] = v[jj];
+                }
+                Peak t;
+                float fsum;
+                thread_peak16(v, lane, half, s, r, t, fsum);
+                t.sum = (double)fsum;
+                peak_merge(cell, t);
+            }
+    }
+    if (rec_out) {
+        rec_out->peak = cell.mx;
+        rec_out->argmax = cell.idx;
+        rec_out->sum = cell.sum;
+        rec_out->count = cell.cnt;
+        rec_out->probe_re = rec_out->probe_im = 0.f;
+        rec_out->pad_ = 0;
     }
     delete w;
     delete wo;

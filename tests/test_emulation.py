@@ -22,17 +22,23 @@ def test_warp_fft1024(emu_lib, inverse):
                                          (16368, 1, 32, -250.0), (1023, 2, 1, 700.0), (3069, 1, 19, 10000.0)])
 def test_polyphase_correlation_matches_oracle(emu_lib, n, n_ms, sv, f):
     emu_lib.emu_cell_profile.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
-                                         ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+                                         ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    rec = np.zeros(1, dtype=[("peak", "<f4"), ("argmax", "<i4"), ("sum", "<f8"), ("count", "<i4"), ("pr", "<f4"),
+                             ("pi", "<f4"), ("pad", "<i4")])
     fs = n * 1000
     iq = o.synth_iq(1, n, n_ms, fs, [(sv, f + 3, n - 7, 0.3, 0.3)])
     chips = o.ca_code(sv).astype(np.uint8)
     prn = o.replica(sv, n)
     nc = np.zeros(n, np.float32)
-    emu_lib.emu_cell_profile(iq.ctypes.data, n, n_ms, float(fs), float(f), chips.ctypes.data, 2, nc.ctypes.data)
+    emu_lib.emu_cell_profile(iq.ctypes.data, n, n_ms, float(fs), float(f), chips.ctypes.data, 2, nc.ctypes.data, rec.ctypes.data)
     ref = o.integrate(o.NON_COHERENT, iq, fs, n, f, prn)
     assert np.abs(nc - ref).max() <= 1e-6 * ref.max()
     assert nc.argmax() == ref.argmax() == n - 7
+    # the branch-free per-thread reduction + merges reproduce np.max / np.argmax / count / sum of the profile
+    assert rec["peak"][0] == nc.max() and rec["argmax"][0] == int(nc.argmax())
+    assert rec["count"][0] == int(np.count_nonzero(nc == nc.max()))
+    assert abs(rec["sum"][0] - nc.astype(np.float64).sum()) <= 2e-6 * rec["sum"][0]
     co = np.zeros(n, np.complex64)
-    emu_lib.emu_cell_profile(iq.ctypes.data, n, n_ms, float(fs), float(f), chips.ctypes.data, 1, co.ctypes.data)
+    emu_lib.emu_cell_profile(iq.ctypes.data, n, n_ms, float(fs), float(f), chips.ctypes.data, 1, co.ctypes.data, None)
     refc = o.integrate(o.COHERENT, iq, fs, n, f, prn)
     assert np.abs(co - refc).max() <= 1e-6 * np.abs(refc).max()
