@@ -184,3 +184,17 @@ void emu_cell_profile(const float2* iq, int N, int n_ms, double fs, double doppl
     delete wo;
 }
 }
+
+// ---- scalar tracking loop (tracker_core.cuh) on the host ----
+#include "../../gypsum_b200/csrc/tracker_core.cuh"
+extern "C" {
+int emu_track_state_size() { return (int)sizeof(TrackState); }
+void emu_track_init(TrackState* st, int prn, double doppler, double carrier_phase, int code_phase) {
+    track_state_init(*st, prn, doppler, carrier_phase, code_phase);
+}
+void emu_track_update(TrackState* st, const float* elp /* E.re E.im L.re L.im P.re P.im */, float strength, int off,
+                      double t0, double fs, TrackMsRecord* out) {
+    track_update(*st, make_float2(elp[0], elp[1]), make_float2(elp[2], elp[3]), make_float2(elp[4], elp[5]), strength, off,
+                 t0, fs, *out);
+}
+}

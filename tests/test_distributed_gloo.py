@@ -1,0 +1,84 @@
+"""N > 1 host logic under gloo on the CPU (world_size 2 and 3): PRN sharding, the single broadcast and the gather
+order of ShardedGridSearch, with a CPU stand-in for the engine (the oracle computes each rank's rows)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_range_partitions():
+    from gypsum_b200.distributed import shard_range
+
+    for n in (0, 1, 5, 32, 1000):
+        for world in (1, 2, 3, 8):
+            parts = [list(shard_range(n, r, world)) for r in range(world)]
+            assert sum(parts, []) == list(range(n))
+            assert max(map(len, parts)) - min(map(len, parts)) <= 1
+
+
+class _OracleEngine:
+    """CPU stand-in with the engine methods ShardedGridSearch uses; 'device pointers' are torch CPU tensors."""
+    samples_per_ms = 2046
+
+    def __init__(self):
+        self.iq = None
+
+    def bind_iq_device(self, ptr, n):
+        import ctypes
+        self.iq = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_float)), shape=(2 * n,)).view(np.complex64).copy()
+
+    def acquire_grid_device(self, n_blocks, ms, prn, dop, kind, out_ptr):
+        import ctypes
+        from gypsum_b200._native import RECORD_DTYPE
+        from oracle import gypsum_oracle as o
+
+        n = self.samples_per_ms
+        rec = np.zeros((n_blocks, prn.size, dop.size), dtype=RECORD_DTYPE)
+        for b in range(n_blocks):
+            peak, arg, total, count = o.grid_cells(self.iq[b * ms * n:(b + 1) * ms * n], n * 1000, n, [int(p) + 1 for p in prn], list(dop))
+            rec[b]["peak"], rec[b]["argmax"], rec[b]["sum"], rec[b]["count"] = peak, arg, total, count
+        ctypes.memmove(out_ptr, rec.ctypes.data, rec.nbytes)
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from gypsum_b200.distributed import ShardedGridSearch
+    from oracle import gypsum_oracle as o
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    x = o.synth_iq(4, 2046, 2, 2046000, [(5, 1000.0, 99, 0.0, 0.4)]) if rank == 0 else None
+    search = ShardedGridSearch(_OracleEngine(), "cpu")
+    full = search.acquire_grid(x, 2, 1, np.arange(5), [0.0, 1000.0], 2)
+    q.put((rank, full["peak"].copy(), full["argmax"].copy()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_grid_search_matches_single_process(world):
+    from oracle import gypsum_oracle as o
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    x = o.synth_iq(4, 2046, 2, 2046000, [(5, 1000.0, 99, 0.0, 0.4)])
+    for b in range(2):
+        peak, arg, _, _ = o.grid_cells(x[b * 2046:(b + 1) * 2046], 2046000, 2046, [1, 2, 3, 4, 5], [0.0, 1000.0])
+        for rank, pk, ag in got:  # every rank ends up with the full, correctly ordered table
+            assert np.allclose(pk[b], peak, rtol=1e-6) and np.array_equal(ag[b], arg)
+    assert got[0][2][0, 4, 1] == 99
