@@ -18,6 +18,13 @@ RECORD_DTYPE = np.dtype(
      ("reserved", "<i4")]
 )
 assert RECORD_DTYPE.itemsize == 32
+TRACK_DTYPE = np.dtype(
+    [("doppler", "<f8"), ("carrier_phase", "<f8"), ("error", "<f8"), ("disc", "<f8"), ("phase_acc", "<f8"),
+     ("peak_re", "<f4"), ("peak_im", "<f4"), ("strength", "<f4"), ("early_re", "<f4"), ("early_im", "<f4"),
+     ("late_re", "<f4"), ("late_im", "<f4"), ("code_phase", "<i4"), ("symbol", "<i4"), ("locked", "<i4"), ("lost", "<i4"),
+     ("peak_offset", "<i4"), ("reserved0", "<i4"), ("reserved1", "<i4")]
+)
+assert TRACK_DTYPE.itemsize == 96
 
 # every symbol include/gypsum_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
@@ -34,6 +41,13 @@ SYMBOLS = {
     "gb200_acquire_grid_device": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P]),
     "gb200_acquire_cells": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P]),
     "gb200_correlation_profile": (C.c_int, [_P, C.c_int, C.c_double, C.c_int, C.c_int, _P]),
+    "gb200_tracker_create": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.POINTER(_P)]),
+    "gb200_tracker_destroy": (C.c_int, [_P]),
+    "gb200_tracker_process": (C.c_int, [_P, C.c_int, _P, _P, _P]),
+    "gb200_tracker_process_device": (C.c_int, [_P, C.c_int, _P, _P]),
+    "gb200_tracker_get_state": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "gb200_tracker_set_state": (C.c_int, [_P, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int32]),
     "gb200_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "gb200_enable_kernel_timing": (C.c_int, [_P, C.c_int]),
     "gb200_kernel_timing": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
@@ -181,6 +195,62 @@ class Engine:
             "gb200_correlation_profile",
         )
         return out.view(np.complex64) if kind == COHERENT else out
+
+
+class Tracker:
+    """A bank of tracking channels on one engine (gb200_tracker_*).  Channels consume the engine's loaded IQ."""
+
+    def __init__(self, engine: Engine, prn_idx, doppler_hz, carrier_phase, code_phase):
+        self._engine = engine
+        self._lib = engine._lib
+        prn = np.ascontiguousarray(prn_idx, dtype=np.int32)
+        dop = np.ascontiguousarray(doppler_hz, dtype=np.float64)
+        cph = np.ascontiguousarray(carrier_phase, dtype=np.float64)
+        code = np.ascontiguousarray(code_phase, dtype=np.int32)
+        if not (prn.shape == dop.shape == cph.shape == code.shape) or prn.ndim != 1:
+            raise ValueError("per-channel arrays must be 1-D and the same length")
+        self.n_channels = prn.size
+        self._h = _P()
+        engine._check(self._lib.gb200_tracker_create(engine._h, prn.size, _ptr(prn), _ptr(dop), _ptr(cph), _ptr(code),
+                                                     C.byref(self._h)), "gb200_tracker_create")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and getattr(self._engine, "_h", None):
+            self._lib.gb200_tracker_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def process(self, n_ms: int, start_times, want_profiles: bool = False):
+        """Records [n_channels, n_ms] (TRACK_DTYPE) and, optionally, |prompt profile| [n_channels, n_ms, N]."""
+        ts = np.ascontiguousarray(start_times, dtype=np.float64)
+        if ts.shape != (n_ms,):
+            raise ValueError("start_times must hold one timestamp per millisecond")
+        out = np.empty((self.n_channels, n_ms), dtype=TRACK_DTYPE)
+        prof = np.empty((self.n_channels, n_ms, self._engine.samples_per_ms), dtype=np.float32) if want_profiles else None
+        self._engine._check(
+            self._lib.gb200_tracker_process(self._h, n_ms, _ptr(ts), _ptr(out), None if prof is None else _ptr(prof)),
+            "gb200_tracker_process")
+        return (out, prof) if want_profiles else out
+
+    def process_device(self, n_ms: int, start_times: np.ndarray, out_device_ptr: int) -> None:
+        self._engine._check(self._lib.gb200_tracker_process_device(self._h, n_ms, _ptr(start_times), _P(out_device_ptr)),
+                            "gb200_tracker_process_device")
+
+    def get_state(self, channel: int) -> dict:
+        d, c, a = C.c_double(), C.c_double(), C.c_double()
+        p, lost = C.c_int32(), C.c_int32()
+        self._engine._check(self._lib.gb200_tracker_get_state(self._h, channel, C.byref(d), C.byref(c), C.byref(a), C.byref(p),
+                                                              C.byref(lost)), "gb200_tracker_get_state")
+        return {"doppler": d.value, "carrier_phase": c.value, "phase_acc": a.value, "code_phase": p.value, "lost": lost.value}
+
+    def set_state(self, channel: int, doppler: float, carrier_phase: float, phase_acc: float, code_phase: int) -> None:
+        self._engine._check(self._lib.gb200_tracker_set_state(self._h, channel, float(doppler), float(carrier_phase),
+                                                              float(phase_acc), int(code_phase)), "gb200_tracker_set_state")
 
 
 def strength_from_records(rec: np.ndarray, n: int) -> np.ndarray:

@@ -2,6 +2,7 @@
 // Host side of the reference path it replaces: gypsum/acquisition.py:154-219 (the per-bin scan and its memo
 // wrapper) and gypsum/utils.py:77-108.
 #include <algorithm>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -97,6 +98,19 @@ struct gb200_engine {
     size_t ev_used[2] = {0, 0};
     std::string err;
 };
+
+struct gb200_tracker {
+    gb200_engine* e = nullptr;
+    int n_channels = 0;
+    DevBuf<TrackState> states;
+    DevBuf<TrackMsRecord> d_out;
+    DevBuf<double> d_times;
+    DevBuf<float> d_prof;
+    PinnedBuf<TrackMsRecord> h_out;
+    PinnedBuf<double> h_times;
+    PinnedBuf<float> h_prof;
+};
+static_assert(sizeof(gb200_track_record) == sizeof(TrackMsRecord), "ABI track record and device record must match");
 
 #define GB_FAIL(e, code, ...)                        \
     do {                                             \
@@ -604,6 +618,156 @@ int gb200_kernel_timing(gb200_engine* e, int which, double* total_ms, int64_t* l
     }
     *total_ms = t;
     *launches = static_cast<int64_t>(e->ev_used[which]);
+    return GB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// tracking
+// ---------------------------------------------------------------------------------------------------------
+int gb200_tracker_create(gb200_engine* e, int n_channels, const int32_t* prn_idx, const double* doppler_hz,
+                         const double* carrier_phase, const int32_t* code_phase, gb200_tracker** out) {
+    if (!e) return GB200_EINVAL;
+    if (!out) GB_FAIL(e, GB200_EINVAL, "null output");
+    *out = nullptr;
+    if (n_channels < 1 || !prn_idx || !doppler_hz || !carrier_phase || !code_phase) GB_FAIL(e, GB200_EINVAL, "no channels");
+    if (e->s != 2 && e->s != 4) GB_FAIL(e, GB200_EINVAL, "tracking needs 2046 or 4092 samples per ms (reference tracker.py:301 hard-wires 2046)");
+    if (e->n_prn == 0) GB_FAIL(e, GB200_ESTATE, "no PRN replicas loaded (gb200_set_replicas)");
+    for (int c = 0; c < n_channels; ++c)
+        if (prn_idx[c] < 0 || prn_idx[c] >= e->n_prn) GB_FAIL(e, GB200_EINVAL, "prn index %d out of range", prn_idx[c]);
+    GB_CUDA(e, cudaSetDevice(e->device));
+    GB_CUDA(e, configure_track_kernel());
+    gb200_tracker* t = new gb200_tracker;
+    t->e = e;
+    t->n_channels = n_channels;
+    std::vector<TrackState> init(n_channels);
+    for (int c = 0; c < n_channels; ++c) {
+        memset(&init[c], 0, sizeof(TrackState));
+        track_state_init(init[c], prn_idx[c], doppler_hz[c], carrier_phase[c], code_phase[c]);
+    }
+    cudaError_t ce = t->states.ensure(n_channels);
+    if (ce == cudaSuccess) ce = cudaMemcpy(t->states.p, init.data(), sizeof(TrackState) * n_channels, cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) {
+        delete t;
+        cudaGetLastError();
+        GB_FAIL(e, GB200_ECUDA, "tracker state allocation failed: %s", cudaGetErrorString(ce));
+    }
+    *out = t;
+    return GB200_OK;
+}
+
+int gb200_tracker_destroy(gb200_tracker* t) {
+    if (!t) return GB200_OK;
+    cudaSetDevice(t->e->device);
+    cudaStreamSynchronize(t->e->stream);
+    t->states.release();
+    t->d_out.release();
+    t->d_times.release();
+    t->d_prof.release();
+    t->h_out.release();
+    t->h_times.release();
+    t->h_prof.release();
+    delete t;
+    return GB200_OK;
+}
+
+static int tracker_launch(gb200_tracker* t, int n_ms, const double* start_times, TrackMsRecord* out_dev, float* prof_dev) {
+    gb200_engine* e = t->e;
+    if (n_ms < 1 || !start_times) GB_FAIL(e, GB200_EINVAL, "need at least one whole millisecond of samples");
+    if (!e->iq) GB_FAIL(e, GB200_ESTATE, "no IQ loaded (gb200_upload_iq / gb200_bind_iq_device)");
+    if (static_cast<int64_t>(n_ms) * e->N > e->iq_samples)
+        GB_FAIL(e, GB200_EINVAL, "need %lld samples, %lld loaded", static_cast<long long>(n_ms) * e->N,
+                static_cast<long long>(e->iq_samples));
+    if (reinterpret_cast<uintptr_t>(e->iq) % 16 != 0) GB_FAIL(e, GB200_EINVAL, "IQ buffer must be 16-byte aligned for tracking");
+    GB_CUDA(e, cudaStreamSynchronize(e->stream));  // h_times may still be in flight
+    GB_CUDA(e, t->d_times.ensure(n_ms));
+    GB_CUDA(e, t->h_times.ensure(n_ms));
+    memcpy(t->h_times.p, start_times, sizeof(double) * n_ms);
+    GB_CUDA(e, cudaMemcpyAsync(t->d_times.p, t->h_times.p, sizeof(double) * n_ms, cudaMemcpyHostToDevice, e->stream));
+    TrackArgs a{};
+    a.iq = e->iq;
+    a.start_times = t->d_times.p;
+    a.states = t->states.p;
+    a.out = out_dev;
+    a.profiles = prof_dev;
+    a.crep = e->crep.p;
+    a.tw1 = e->tw1.p;
+    a.tw2 = e->tw2.p;
+    a.fs = static_cast<double>(e->fs);
+    a.inv_fs = 1.0 / static_cast<double>(e->fs);
+    a.N = e->N;
+    a.s = e->s;
+    a.n_ms = n_ms;
+    a.n_channels = t->n_channels;
+    GB_CUDA(e, launch_track_channels(a, e->stream));
+    e->launches++;
+    return GB200_OK;
+}
+
+int gb200_tracker_process_device(gb200_tracker* t, int n_ms, const double* start_times, void* out_device) {
+    if (!t) return GB200_EINVAL;
+    gb200_engine* e = t->e;
+    if (!out_device) GB_FAIL(e, GB200_EINVAL, "null output");
+    GB_CUDA(e, cudaSetDevice(e->device));
+    return tracker_launch(t, n_ms, start_times, static_cast<TrackMsRecord*>(out_device), nullptr);
+}
+
+int gb200_tracker_process(gb200_tracker* t, int n_ms, const double* start_times, gb200_track_record* out_host,
+                          float* profiles_host) {
+    if (!t) return GB200_EINVAL;
+    gb200_engine* e = t->e;
+    if (!out_host) GB_FAIL(e, GB200_EINVAL, "null output");
+    GB_CUDA(e, cudaSetDevice(e->device));
+    if (n_ms < 1) GB_FAIL(e, GB200_EINVAL, "need at least one whole millisecond of samples");
+    const size_t n = static_cast<size_t>(t->n_channels) * n_ms;
+    GB_CUDA(e, t->d_out.ensure(n));
+    GB_CUDA(e, t->h_out.ensure(n));
+    const size_t np = profiles_host ? n * e->N : 0;
+    if (np) {
+        GB_CUDA(e, t->d_prof.ensure(np));
+        GB_CUDA(e, t->h_prof.ensure(np));
+    }
+    int rc = tracker_launch(t, n_ms, start_times, t->d_out.p, np ? t->d_prof.p : nullptr);
+    if (rc) return rc;
+    GB_CUDA(e, cudaMemcpyAsync(t->h_out.p, t->d_out.p, n * sizeof(TrackMsRecord), cudaMemcpyDeviceToHost, e->stream));
+    if (np) GB_CUDA(e, cudaMemcpyAsync(t->h_prof.p, t->d_prof.p, np * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    GB_CUDA(e, cudaStreamSynchronize(e->stream));
+    memcpy(out_host, t->h_out.p, n * sizeof(TrackMsRecord));
+    if (np) memcpy(profiles_host, t->h_prof.p, np * sizeof(float));
+    return GB200_OK;
+}
+
+int gb200_tracker_get_state(gb200_tracker* t, int channel, double* doppler_hz, double* carrier_phase, double* phase_acc,
+                            int32_t* code_phase, int32_t* lost) {
+    if (!t) return GB200_EINVAL;
+    gb200_engine* e = t->e;
+    if (channel < 0 || channel >= t->n_channels) GB_FAIL(e, GB200_EINVAL, "channel %d out of range", channel);
+    GB_CUDA(e, cudaSetDevice(e->device));
+    GB_CUDA(e, cudaStreamSynchronize(e->stream));
+    TrackState st;
+    GB_CUDA(e, cudaMemcpy(&st, t->states.p + channel, offsetof(TrackState, err_ring), cudaMemcpyDeviceToHost));
+    if (doppler_hz) *doppler_hz = st.doppler;
+    if (carrier_phase) *carrier_phase = st.carrier_phase;
+    if (phase_acc) *phase_acc = st.phase_acc;
+    if (code_phase) *code_phase = st.code_phase;
+    if (lost) *lost = st.lost;
+    return GB200_OK;
+}
+
+int gb200_tracker_set_state(gb200_tracker* t, int channel, double doppler_hz, double carrier_phase, double phase_acc,
+                            int32_t code_phase) {
+    if (!t) return GB200_EINVAL;
+    gb200_engine* e = t->e;
+    if (channel < 0 || channel >= t->n_channels) GB_FAIL(e, GB200_EINVAL, "channel %d out of range", channel);
+    GB_CUDA(e, cudaSetDevice(e->device));
+    GB_CUDA(e, cudaStreamSynchronize(e->stream));
+    TrackState st;
+    const size_t head = offsetof(TrackState, err_ring);
+    GB_CUDA(e, cudaMemcpy(&st, t->states.p + channel, head, cudaMemcpyDeviceToHost));
+    st.doppler = doppler_hz;
+    st.carrier_phase = carrier_phase;
+    st.phase_acc = phase_acc;
+    st.code_phase = code_phase;
+    GB_CUDA(e, cudaMemcpy(t->states.p + channel, &st, head, cudaMemcpyHostToDevice));
     return GB200_OK;
 }
 

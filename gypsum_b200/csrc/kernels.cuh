@@ -1,6 +1,7 @@
 // Kernel argument blocks and launch wrappers (implemented in kernels.cu, used by engine.cu).
 #pragma once
 #include "gb_common.cuh"
+#include "tracker_core.cuh"
 
 namespace gb {
 
@@ -42,6 +43,23 @@ struct CorrelateArgs {
     const int* cell_probe;  // coherent probe index or -1 (both modes, indexed by output slot; may be null)
 };
 
+// track_channels: one persistent CTA per channel.
+struct TrackArgs {
+    const float2* iq;           // [n_ms * N] the stream every channel consumes
+    const double* start_times;  // [n_ms] chunk start timestamps (antenna_sample_provider.py:88-89)
+    TrackState* states;         // [n_channels]
+    TrackMsRecord* out;         // [n_channels][n_ms]
+    float* profiles;            // optional [n_channels][n_ms][N]: |prompt profile| (tracker.py:308-309)
+    const float2* crep;
+    const float2* tw1;
+    const float2* tw2;
+    double fs, inv_fs;
+    int N, s, n_ms, n_channels;
+};
+
+size_t track_smem_bytes(int N, int s);
+cudaError_t configure_track_kernel();
+cudaError_t launch_track_channels(const TrackArgs& a, cudaStream_t st);
 size_t spectra_smem_bytes(int s);
 size_t correlate_smem_bytes(int np);
 cudaError_t launch_init_tables(float2* tw1, float2* tw2, cudaStream_t st);

@@ -89,6 +89,50 @@ int gb200_acquire_cells(gb200_engine* e, int n_cells, const int32_t* prn_idx, co
 int gb200_correlation_profile(gb200_engine* e, int prn_idx, double doppler_hz, int n_ms, int integration_type,
                               float* out_host);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Tracking (gypsum/tracker.py).  A tracker is a bank of channels sharing the engine's loaded IQ stream; every
+ * channel is one GpsSatelliteTracker (tracker.py:206-389): state {Doppler, carrier phase, code phase} seeded
+ * from an acquisition result (satellite_signal_processing_pipeline.py:56-62).
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct gb200_tracker gb200_tracker;
+
+/* One millisecond of one channel (96 bytes): what GpsSatelliteTracker.process_samples (tracker.py:331-389)
+ * leaves in tracking_params' histories plus the emitted pseudosymbol.                                        */
+typedef struct gb200_track_record {
+    double doppler;        /* current_doppler_shift after this ms            (tracker.py:260, :352)          */
+    double carrier_phase;  /* current_carrier_wave_phase_shift after this ms (tracker.py:258-259, :353)       */
+    double error;          /* Costas discriminator I*Q                       (tracker.py:249, :261)           */
+    double disc;           /* (|E|^2 - |L|^2) / 2                            (tracker.py:297, :300)           */
+    double phase_acc;      /* self.phase after the update                    (tracker.py:298-303)             */
+    float peak_re, peak_im; /* coherent prompt correlation peak              (tracker.py:313, :346)           */
+    float strength;        /* get_normalized_correlation_peak_strength       (tracker.py:311, :347)           */
+    float early_re, early_im, late_re, late_im; /* np.correlate taps         (tracker.py:293-295)             */
+    int32_t code_phase;    /* current_prn_code_phase_shift after this ms     (tracker.py:299)                 */
+    int32_t symbol;        /* sign(Re peak): +1 / -1 (0 only if Re peak == 0) (tracker.py:316)                */
+    int32_t locked;        /* is_locked() used for this ms's loop bandwidth  (tracker.py:251)                 */
+    int32_t lost;          /* 1: LostSatelliteLockError raised at this ms (tracker.py:378); 2: channel already stopped */
+    int32_t peak_offset;   /* np.argmax of the prompt profile                (tracker.py:310)                 */
+    int32_t reserved[2];
+} gb200_track_record;
+
+/* satellite_signal_processing_pipeline.py:56-63: one channel per (replica row, Doppler, carrier phase, code
+ * phase).  Needs samples_per_ms == 2046 or 4092 (the reference hard-wires 2046, tracker.py:301-303,319).     */
+int gb200_tracker_create(gb200_engine* e, int n_channels, const int32_t* prn_idx, const double* doppler_hz,
+                         const double* carrier_phase, const int32_t* code_phase, gb200_tracker** out);
+int gb200_tracker_destroy(gb200_tracker* t);
+/* tracker.py:331 process_samples for n_ms consecutive 1-ms chunks of the engine's loaded IQ, every channel.
+ * start_times[n_ms]: AntennaSampleChunk.start_time of each chunk.  out_host[channel*n_ms + ms].
+ * profiles_host (may be NULL): [channel][ms][N] |prompt correlation profile| (tracker.py:309), float32.      */
+int gb200_tracker_process(gb200_tracker* t, int n_ms, const double* start_times, gb200_track_record* out_host,
+                          float* profiles_host);
+/* Enqueue only; records stay on the device (out_device: n_channels*n_ms records). */
+int gb200_tracker_process_device(gb200_tracker* t, int n_ms, const double* start_times, void* out_device);
+/* Read / overwrite the loop state of one channel (tracking_params.current_* and tracker.phase). */
+int gb200_tracker_get_state(gb200_tracker* t, int channel, double* doppler_hz, double* carrier_phase, double* phase_acc,
+                            int32_t* code_phase, int32_t* lost);
+int gb200_tracker_set_state(gb200_tracker* t, int channel, double doppler_hz, double carrier_phase, double phase_acc,
+                            int32_t code_phase);
+
 /* Kernels launched by this engine so far (bench.py's gpu_launches). */
 int gb200_launch_count(const gb200_engine* e, int64_t* out);
 
