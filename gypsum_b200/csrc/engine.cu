@@ -428,7 +428,7 @@ int gb200_create(int device, int fs, int n, gb200_engine** out) {
     e->N = n;
     e->s = n / kChips;
     e->spec_budget_bytes = static_cast<size_t>(env_int("GB200_SPEC_BUDGET_MB", 80)) << 20;
-    e->np = 8;
+    e->np = env_int("GB200_NP", 8) == 10 ? 10 : 8;
     e->rsplit_override = env_int("GB200_RSPLIT", 0);
     auto fail = [&](cudaError_t c, const char* what) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(c);
@@ -445,8 +445,8 @@ int gb200_create(int device, int fs, int n, gb200_engine** out) {
         return GB200_ECUDA;
     }
     e->num_sms = prop.multiProcessorCount;
-    if (spectra_smem_bytes(e->s) > 200 * 1024) {
-        g_create_error = "samples_per_ms too large for the shared-memory polyphase buffer";
+    if (!spectra_supports(e->s)) {
+        g_create_error = "samples_per_ms / 1023 must be one of 1,2,3,4,5,6,8,10,12,16";
         delete e;
         return GB200_EINVAL;
     }

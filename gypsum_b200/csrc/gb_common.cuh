@@ -16,7 +16,8 @@ namespace gb {
 constexpr int kChips = 1023;   // constants.py:7  PRN_CHIP_COUNT
 constexpr int kFft = 1024;     // one warp-level transform
 constexpr int kPad = 2048;     // zero-padded length carrying a length-1023 circular correlation (>= 2*1023-1)
-constexpr int kTStride = 33;   // padded row of the 32x32 transpose tile (float2 units): conflict-free both ways
+constexpr int kTStride = 34;   // padded row of the 32x32 transpose tile (float2 units): 16-byte aligned rows, conflict-free
+                               // for the 64-bit column writes and the 128-bit row reads
 constexpr int kTileF2 = 32 * kTStride;
 
 // Result of reducing one correlation profile; mirrors include/gypsum_b200.h gb200_cell_record (32 bytes).

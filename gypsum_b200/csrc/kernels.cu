@@ -24,12 +24,12 @@ __global__ void k_init_tables(float2* tw1, float2* tw2) {
         const int k1 = t >> 5, l = t & 31;
         double s, c;
         sincospi(-2.0 * ((l * k1) & 1023) / 1024.0, &s, &c);
-        tw1[t] = make_float2(static_cast<float>(c), static_cast<float>(s));
+        tw1[pidx(k1, l)] = make_float2(static_cast<float>(c), static_cast<float>(s));
     }
     {
         double s, c;
         sincospi(-2.0 * t / 2048.0, &s, &c);
-        tw2[t] = make_float2(static_cast<float>(c), static_cast<float>(s));
+        tw2[zpos(t)] = make_float2(static_cast<float>(c), static_cast<float>(s));
     }
 }
 
@@ -49,52 +49,74 @@ __global__ void __launch_bounds__(128) k_replica_spectra(const uint8_t* chips, f
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     double re, im;
     replica_spectrum_bin(c, g, cs, re, im);
-    crep[(static_cast<size_t>(p) * 2 + (g & 1)) * kFft + (g >> 1)] = make_float2(static_cast<float>(re), static_cast<float>(im));
+    crep[(static_cast<size_t>(p) * 2 + (g & 1)) * kFft + zpos(g >> 1)] = make_float2(static_cast<float>(re), static_cast<float>(im));
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // doppler_spectra
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kSpecWarps = 4;
+constexpr int kSpecWarps = 8;
+constexpr int kSpecThreads = kSpecWarps * 32;
+constexpr int kCarrierTable = 64;  // ceil(16368 / 256)
 
-__global__ void __launch_bounds__(kSpecWarps * 32) k_doppler_spectra(const SpectraArgs a) {
-    const float2* __restrict__ tw1 = a.tw1;
-    const float2* __restrict__ tw2 = a.tw2;
+template <int S>
+__global__ void __launch_bounds__(kSpecThreads) k_doppler_spectra(const SpectraArgs a) {
     extern __shared__ __align__(16) float2 smem[];
-    float2* ypoly = smem;                                   // [s][1024]
-    float2* tiles = smem + static_cast<size_t>(a.s) * kFft;  // [kSpecWarps][kTileF2]
+    float2* ypoly = smem;                          // [S][1024], rows in zpos() order
+    float2* tiles = smem + S * kFft;               // [kSpecWarps][kTileF2]
+    float2* coarse = tiles + kSpecWarps * kTileF2;  // [kCarrierTable] carrier at samples 0, 256, 512, ...
 
     const int unit = blockIdx.x / a.M, i = blockIdx.x % a.M;
     const int b = unit / a.n_doppler, d = unit % a.n_doppler;
     const double f = a.doppler[d];
     const float2* __restrict__ src = a.iq + static_cast<size_t>(b) * a.block_stride + static_cast<size_t>(i) * a.N;
+    const int tid = threadIdx.x;
 
-    // Wipe-off, coalesced float2 loads of the 1-ms IQ vector; stored de-interleaved by polyphase branch.
-    for (int n = threadIdx.x; n < a.N; n += blockDim.x) {
-        const float2 x = src[n];
-        const double cyc = f * (static_cast<double>(n + i * a.N) * a.inv_fs);
-        const int row = n % a.s, col = n / a.s;
-        ypoly[row * kFft + col] = wipeoff(x, cyc);
+    // Carrier exp(-j 2 pi f (n + i N)/fs) (utils.py:93-96) as coarse[n / 256] * fine[n % 256]: both factors get an
+    // exact float64-reduced phase, so there is one sincos per thread instead of one per sample and no recurrence
+    // error growth.
+    const int n_coarse = (a.N + kSpecThreads - 1) / kSpecThreads;
+    if (tid < n_coarse) coarse[tid] = carrier_at(f, static_cast<double>(tid * kSpecThreads + i * a.N), a.inv_fs);
+    const float2 fine = carrier_at(f, static_cast<double>(tid), a.inv_fs);
+    __syncthreads();
+    // coalesced float2 loads of the 1-ms IQ vector; wipe-off; de-interleave by polyphase branch
+    for (int k = 0, n = tid; n < a.N; ++k, n += kSpecThreads) {
+        const float2 y = cmul(src[n], cmul(coarse[k], fine));
+        ypoly[(n % S) * kFft + zpos(n / S)] = y;
     }
     __syncthreads();
-    if (threadIdx.x < a.s) ypoly[threadIdx.x * kFft + (kFft - 1)] = ypoly[threadIdx.x * kFft];
+    if (tid < S) ypoly[tid * kFft + zpos(kFft - 1)] = ypoly[tid * kFft + zpos(0)];
+    __syncthreads();
+    // in place: rows of y -> rows of boxcar sums z_r (column 1023 is never read as data)
+    if (S > 1) {
+        for (int m0 = 0; m0 < kChips; m0 += kSpecThreads) {
+            const int m = m0 + tid;
+            float2 z[S];
+            if (m < kChips) boxcar_column<S>(ypoly, m, z);
+            __syncthreads();
+            if (m < kChips) {
+#pragma unroll
+                for (int r = 0; r < S; ++r) ypoly[r * kFft + zpos(m)] = z[r];
+            }
+        }
+        __syncthreads();
+    }
+    if (tid < S) ypoly[tid * kFft + zpos(kFft - 1)] = make_float2(0.f, 0.f);  // zero padding of the 1023-point input
     __syncthreads();
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = tid >> 5, lane = tid & 31;
     float2* tile = tiles + warp * kTileF2;
-    float2* __restrict__ dst0 = a.spec + (static_cast<size_t>(unit) * a.M + i) * a.s * 2 * kFft;
-    for (int task = warp; task < 2 * a.s; task += kSpecWarps) {
+    float2* __restrict__ dst0 = a.spec + (static_cast<size_t>(unit) * a.M + i) * S * 2 * kFft;
+    for (int task = warp; task < 2 * S; task += kSpecWarps) {
         const int r = task >> 1, half = task & 1;
         float re[32], im[32];
-        build_z(re, im, lane, r, a.s, ypoly);
-        if (half) mul_tw2(re, im, lane, tw2);
-        wfft_phase1(re, im, lane, tw1, tile);
+        load_vec(re, im, lane, ypoly + r * kFft);
+        if (half) mul_tw2(re, im, lane, a.tw2);
+        wfft_phase1(re, im, lane, a.tw1, tile);
         __syncwarp();
         wfft_phase2(re, im, lane, tile);
         __syncwarp();
-        float2* __restrict__ dst = dst0 + static_cast<size_t>(task) * kFft;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) dst[j * 32 + lane] = make_float2(re[j], im[j]);
+        store_vec(re, im, lane, dst0 + static_cast<size_t>(task) * kFft);
     }
 }
 
@@ -125,7 +147,7 @@ __device__ __forceinline__ void warp_reduce_peak(Peak& p) {
 }
 
 template <int NP, int KIND, bool PROFILE>
-__global__ void __launch_bounds__(NP * 64, (NP == 8 ? 1 : 2)) k_correlate_cells(const CorrelateArgs a) {
+__global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateArgs a) {
     extern __shared__ __align__(16) float2 smem[];
     float2* crep_s = smem;                 // [2][1024]
     float2* tw1_s = crep_s + 2 * kFft;     // [32][32]
@@ -232,26 +254,19 @@ __global__ void __launch_bounds__(NP * 64, (NP == 8 ? 1 : 2)) k_correlate_cells(
                         for (int i = 0; i < a.M; ++i) {
                             const float2* __restrict__ p = spec_u + (static_cast<size_t>(i * a.s + r) * 2 + h) * kFft;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const float2 v = p[j * 32 + lane];
-                                re[j] += v.x;
-                                im[j] += v.y;
+                            for (int jp = 0; jp < 16; ++jp) {
+                                float2 v0, v1;
+                                ld_pair(p + 2 * (jp * 32 + lane), v0, v1);
+                                re[2 * jp] += v0.x;
+                                im[2 * jp] += v0.y;
+                                re[2 * jp + 1] += v1.x;
+                                im[2 * jp + 1] += v1.y;
                             }
                         }
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float2 y = cmul(make_float2(re[j], im[j]), crep_h[j * 32 + lane]);
-                            re[j] = y.x;
-                            im[j] = y.y;
-                        }
+                        mul_vec(re, im, lane, crep_h);
                     } else {
                         const float2* __restrict__ p = spec_u + (static_cast<size_t>(it * a.s + r) * 2 + h) * kFft;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float2 y = cmul(p[j * 32 + lane], crep_h[j * 32 + lane]);
-                            re[j] = y.x;
-                            im[j] = y.y;
-                        }
+                        load_mul_vec(re, im, lane, p, crep_h);
                     }
                     // inverse warp FFT-1024 = forward transform on swapped re/im
                     wfft_phase1(im, re, lane, tw1_s, tile);
@@ -358,24 +373,42 @@ __global__ void __launch_bounds__(NP * 64, (NP == 8 ? 1 : 2)) k_correlate_cells(
 // ---------------------------------------------------------------------------------------------------------
 // launch wrappers
 // ---------------------------------------------------------------------------------------------------------
-size_t spectra_smem_bytes(int s) { return (static_cast<size_t>(s) * kFft + kSpecWarps * kTileF2) * sizeof(float2); }
+size_t spectra_smem_bytes(int s) {
+    return (static_cast<size_t>(s) * kFft + kSpecWarps * kTileF2 + kCarrierTable) * sizeof(float2);
+}
 size_t correlate_smem_bytes(int np) {
     return (4 * static_cast<size_t>(kFft) + 2 * np * kTileF2) * sizeof(float2) + 2 * np * sizeof(PairPartial) + 16;
 }
 
+bool spectra_supports(int s) {
+    switch (s) {
+        case 1: case 2: case 3: case 4: case 5: case 6: case 8: case 10: case 12: case 16: return true;
+        default: return false;
+    }
+}
+
+template <int S>
+static cudaError_t spectra_attr() {
+    return cudaFuncSetAttribute(k_doppler_spectra<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(spectra_smem_bytes(S)));
+}
+template <int NP>
+static cudaError_t correlate_attr() {
+    const int sm = static_cast<int>(correlate_smem_bytes(NP));
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_correlate_cells<NP, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm))) return e;
+    if ((e = cudaFuncSetAttribute(k_correlate_cells<NP, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm))) return e;
+    if ((e = cudaFuncSetAttribute(k_correlate_cells<NP, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm))) return e;
+    return cudaFuncSetAttribute(k_correlate_cells<NP, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+}
+
 cudaError_t configure_kernels() {
     cudaError_t e;
-    e = cudaFuncSetAttribute(k_doppler_spectra, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return e;
-    const int s8 = static_cast<int>(correlate_smem_bytes(8));
-    e = cudaFuncSetAttribute(k_correlate_cells<8, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_correlate_cells<8, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_correlate_cells<8, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_correlate_cells<8, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8);
-    return e;
+#define GB_ATTR(S) if ((e = spectra_attr<S>()) != cudaSuccess) return e;
+    GB_ATTR(1) GB_ATTR(2) GB_ATTR(3) GB_ATTR(4) GB_ATTR(5) GB_ATTR(6) GB_ATTR(8) GB_ATTR(10) GB_ATTR(12) GB_ATTR(16)
+#undef GB_ATTR
+    if ((e = correlate_attr<8>()) != cudaSuccess) return e;
+    return correlate_attr<10>();
 }
 
 cudaError_t launch_init_tables(float2* tw1, float2* tw2, cudaStream_t st) {
@@ -387,20 +420,32 @@ cudaError_t launch_replica_spectra(const uint8_t* chips_dev, int n_prn, float2* 
     return cudaGetLastError();
 }
 cudaError_t launch_doppler_spectra(const SpectraArgs& a, cudaStream_t st) {
-    k_doppler_spectra<<<a.n_units * a.M, kSpecWarps * 32, spectra_smem_bytes(a.s), st>>>(a);
+    const int grid = a.n_units * a.M;
+    const size_t sm = spectra_smem_bytes(a.s);
+    switch (a.s) {
+#define GB_CASE(S) case S: k_doppler_spectra<S><<<grid, kSpecThreads, sm, st>>>(a); break;
+        GB_CASE(1) GB_CASE(2) GB_CASE(3) GB_CASE(4) GB_CASE(5) GB_CASE(6) GB_CASE(8) GB_CASE(10) GB_CASE(12) GB_CASE(16)
+#undef GB_CASE
+        default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
-cudaError_t launch_correlate_cells(const CorrelateArgs& a, int np, int grid, cudaStream_t st) {
-    (void)np;  // one build: 8 warp pairs per CTA, one CTA per SM
-    const size_t sm = correlate_smem_bytes(8);
+
+template <int NP>
+static void correlate_dispatch(const CorrelateArgs& a, int grid, cudaStream_t st) {
+    const size_t sm = correlate_smem_bytes(NP);
     const bool prof = a.profile != nullptr;
     if (a.kind == kKindCoherent) {
-        if (prof) k_correlate_cells<8, 1, true><<<grid, 512, sm, st>>>(a);
-        else k_correlate_cells<8, 1, false><<<grid, 512, sm, st>>>(a);
+        if (prof) k_correlate_cells<NP, 1, true><<<grid, NP * 64, sm, st>>>(a);
+        else k_correlate_cells<NP, 1, false><<<grid, NP * 64, sm, st>>>(a);
     } else {
-        if (prof) k_correlate_cells<8, 2, true><<<grid, 512, sm, st>>>(a);
-        else k_correlate_cells<8, 2, false><<<grid, 512, sm, st>>>(a);
+        if (prof) k_correlate_cells<NP, 2, true><<<grid, NP * 64, sm, st>>>(a);
+        else k_correlate_cells<NP, 2, false><<<grid, NP * 64, sm, st>>>(a);
     }
+}
+cudaError_t launch_correlate_cells(const CorrelateArgs& a, int np, int grid, cudaStream_t st) {
+    if (np == 10) correlate_dispatch<10>(a, grid, st);
+    else correlate_dispatch<8>(a, grid, st);
     return cudaGetLastError();
 }
 

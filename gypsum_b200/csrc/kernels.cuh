@@ -61,6 +61,7 @@ size_t track_smem_bytes(int N, int s);
 cudaError_t configure_track_kernel();
 cudaError_t launch_track_channels(const TrackArgs& a, cudaStream_t st);
 size_t spectra_smem_bytes(int s);
+bool spectra_supports(int s);
 size_t correlate_smem_bytes(int np);
 cudaError_t launch_init_tables(float2* tw1, float2* tw2, cudaStream_t st);
 cudaError_t launch_replica_spectra(const uint8_t* chips_dev, int n_prn, float2* crep, cudaStream_t st);

@@ -121,13 +121,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) k_track_channels(const Track
             __syncwarp();
             wfft_phase2(re, im, lane, tile);
             __syncwarp();
-            const float2* crep_h = crep_s + h * kFft;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float2 y = cmul(make_float2(re[j], im[j]), crep_h[j * 32 + lane]);
-                re[j] = y.x;
-                im[j] = y.y;
-            }
+            mul_vec(re, im, lane, crep_s + h * kFft);
             wfft_phase1(im, re, lane, tw1_s, tile);
             __syncwarp();
             wfft_phase2(im, re, lane, tile);

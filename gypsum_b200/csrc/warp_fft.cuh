@@ -25,27 +25,104 @@ GB_HD GB_INLINE float2 cmulc(float2 a, float2 b) {  // a * conj(b)
     return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
 }
 
+// Pair-interleaved layout used by every per-thread table and vector (spectra, replica spectra, twiddles, exchange
+// tiles, polyphase rows): element j of lane `lane` (i.e. logical index lane + 32 j) sits at pidx(j, lane), so a thread's
+// elements (2jp, 2jp+1) are one aligned 16-byte word and a warp access is 512 contiguous bytes: half the load/store
+// instructions of a float2 layout, still fully coalesced / conflict-free.
+GB_HD GB_INLINE int pidx(int j, int lane) { return (((j >> 1) * 32 + lane) << 1) | (j & 1); }
+GB_HD GB_INLINE int zpos(int m) { return pidx(m >> 5, m & 31); }  // logical index m = lane + 32 j
+
+GB_HD GB_INLINE void ld_pair(const float2* p, float2& a, float2& b) {
+#if defined(__CUDA_ARCH__)
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    a = make_float2(v.x, v.y);
+    b = make_float2(v.z, v.w);
+#else
+    a = p[0];
+    b = p[1];
+#endif
+}
+GB_HD GB_INLINE void st_pair(float2* p, float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<float4*>(p) = make_float4(a.x, a.y, b.x, b.y);
+#else
+    p[0] = a;
+    p[1] = b;
+#endif
+}
+
 // Phase 1 of the forward warp FFT-1024.  re/im[j] = x[lane + 32 j].  Writes u[lane][k1]*W1024^(lane k1) to the
-// tile, row k1, column lane.  tw1[k1*32 + lane] = exp(-2 pi i lane k1 / 1024).
+// tile, row k1, column lane.  tw1[pidx(k1, lane)] = exp(-2 pi i lane k1 / 1024).
 GB_HD GB_INLINE void wfft_phase1(float (&re)[32], float (&im)[32], int lane, const float2* tw1, float2* tile) {
     fft32_fwd(re, im);
-    tile[lane] = make_float2(re[0], im[0]);
 #pragma unroll
-    for (int k1 = 1; k1 < 32; ++k1) {
-        const float2 w = tw1[k1 * 32 + lane];
-        tile[k1 * kTStride + lane] = make_float2(re[k1] * w.x - im[k1] * w.y, re[k1] * w.y + im[k1] * w.x);
+    for (int kp = 0; kp < 16; ++kp) {
+        float2 w0, w1;
+        ld_pair(tw1 + 2 * (kp * 32 + lane), w0, w1);
+        const int k1 = 2 * kp;
+        if (kp == 0) tile[lane] = make_float2(re[0], im[0]);
+        else tile[k1 * kTStride + lane] = make_float2(re[k1] * w0.x - im[k1] * w0.y, re[k1] * w0.y + im[k1] * w0.x);
+        tile[(k1 + 1) * kTStride + lane] =
+            make_float2(re[k1 + 1] * w1.x - im[k1 + 1] * w1.y, re[k1 + 1] * w1.y + im[k1 + 1] * w1.x);
     }
 }
 // Phase 2: thread `lane` owns column k1 = lane: reads u[l][lane], l = 0..31, FFT-32 over l.  Afterwards
 // re/im[k2] = X[lane + 32 k2].
 GB_HD GB_INLINE void wfft_phase2(float (&re)[32], float (&im)[32], int lane, const float2* tile) {
 #pragma unroll
-    for (int l = 0; l < 32; ++l) {
-        const float2 v = tile[lane * kTStride + l];
-        re[l] = v.x;
-        im[l] = v.y;
+    for (int lp = 0; lp < 16; ++lp) {
+        float2 v0, v1;
+        ld_pair(tile + lane * kTStride + 2 * lp, v0, v1);
+        re[2 * lp] = v0.x;
+        im[2 * lp] = v0.y;
+        re[2 * lp + 1] = v1.x;
+        im[2 * lp + 1] = v1.y;
     }
     fft32_fwd(re, im);
+}
+
+// registers <-> a pair-interleaved vector (global or shared)
+GB_HD GB_INLINE void load_vec(float (&re)[32], float (&im)[32], int lane, const float2* v) {
+#pragma unroll
+    for (int jp = 0; jp < 16; ++jp) {
+        float2 a, b;
+        ld_pair(v + 2 * (jp * 32 + lane), a, b);
+        re[2 * jp] = a.x;
+        im[2 * jp] = a.y;
+        re[2 * jp + 1] = b.x;
+        im[2 * jp + 1] = b.y;
+    }
+}
+GB_HD GB_INLINE void store_vec(const float (&re)[32], const float (&im)[32], int lane, float2* v) {
+#pragma unroll
+    for (int jp = 0; jp < 16; ++jp)
+        st_pair(v + 2 * (jp * 32 + lane), make_float2(re[2 * jp], im[2 * jp]), make_float2(re[2 * jp + 1], im[2 * jp + 1]));
+}
+// x[j] *= w[j] for a pair-interleaved vector w (spectrum product, twiddles)
+GB_HD GB_INLINE void mul_vec(float (&re)[32], float (&im)[32], int lane, const float2* w) {
+#pragma unroll
+    for (int jp = 0; jp < 16; ++jp) {
+        float2 a, b;
+        ld_pair(w + 2 * (jp * 32 + lane), a, b);
+        const float r0 = re[2 * jp], i0 = im[2 * jp], r1 = re[2 * jp + 1], i1 = im[2 * jp + 1];
+        re[2 * jp] = r0 * a.x - i0 * a.y;
+        im[2 * jp] = r0 * a.y + i0 * a.x;
+        re[2 * jp + 1] = r1 * b.x - i1 * b.y;
+        im[2 * jp + 1] = r1 * b.y + i1 * b.x;
+    }
+}
+// re/im = a[j] * w[j]: load a pair-interleaved vector and multiply in one pass (half-spectrum x replica spectrum)
+GB_HD GB_INLINE void load_mul_vec(float (&re)[32], float (&im)[32], int lane, const float2* a, const float2* w) {
+#pragma unroll
+    for (int jp = 0; jp < 16; ++jp) {
+        float2 a0, a1, w0, w1;
+        ld_pair(a + 2 * (jp * 32 + lane), a0, a1);
+        ld_pair(w + 2 * (jp * 32 + lane), w0, w1);
+        re[2 * jp] = a0.x * w0.x - a0.y * w0.y;
+        im[2 * jp] = a0.x * w0.y + a0.y * w0.x;
+        re[2 * jp + 1] = a1.x * w1.x - a1.y * w1.y;
+        im[2 * jp + 1] = a1.x * w1.y + a1.y * w1.x;
+    }
 }
 
 // Carrier wipe-off of one sample (utils.py:93-97 / tracker.py:278-281): x * exp(-j 2 pi cycles), with the
@@ -63,8 +140,35 @@ GB_HD GB_INLINE float2 wipeoff(float2 x, double cycles) {
     return make_float2(x.x * c + x.y * s, x.y * c - x.x * s);  // x * (c - j s)
 }
 
-// Polyphase boxcar: z_r[m] for m = lane + 32 j, from the wiped-off millisecond stored as ypoly[t][m'] =
-// y[s*m' + t] with row length 1024 and ypoly[t][1023] = ypoly[t][0] (the circular wrap).
+// exp(-j 2 pi frac(f * idx / fs)): the carrier at sample index idx, phase reduced in float64 first.
+GB_HD GB_INLINE float2 carrier_at(double f, double idx, double inv_fs) { return wipeoff(make_float2(1.f, 0.f), f * (idx * inv_fs)); }
+
+// All s polyphase boxcar sums of column m at once, from rows stored as ypoly[t][zpos(m')] = y[s*m' + t] (row
+// length 1024, column 1023 = copy of column 0 for the circular wrap):
+//     z_r[m] = sum_{t>=r} y[s m + t] + sum_{t<r} y[s (m+1) + t].
+// The caller reads every column of a round, synchronises, then writes z_r[m] back over ypoly[r][zpos(m)].
+template <int S>
+GB_HD GB_INLINE void boxcar_column(const float2* ypoly, int m, float2 (&z)[S]) {
+    float2 v[S], w[S];
+#pragma unroll
+    for (int t = 0; t < S; ++t) {
+        v[t] = ypoly[t * kFft + zpos(m)];
+        w[t] = ypoly[t * kFft + zpos(m + 1)];
+    }
+    float2 suf[S + 1];
+    suf[S] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int t = S - 1; t >= 0; --t) suf[t] = make_float2(suf[t + 1].x + v[t].x, suf[t + 1].y + v[t].y);
+    float2 pre = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < S; ++r) {
+        z[r] = make_float2(suf[r].x + pre.x, suf[r].y + pre.y);
+        pre = make_float2(pre.x + w[r].x, pre.y + w[r].y);
+    }
+}
+
+// Polyphase boxcar computed directly (tracking kernel, s = 2 or 4): z_r[m] for m = lane + 32 j, from the wiped-off
+// millisecond stored linearly as ypoly[t][m'] = y[s*m' + t], row length 1024, ypoly[t][1023] = ypoly[t][0].
 GB_HD GB_INLINE void build_z(float (&re)[32], float (&im)[32], int lane, int r, int s, const float2* ypoly) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -84,16 +188,9 @@ GB_HD GB_INLINE void build_z(float (&re)[32], float (&im)[32], int lane, int r, 
     }
 }
 
-// x[n] *= W2048^n (forward odd half) for n = lane + 32 j;  tw2[n] = exp(-2 pi i n / 2048), n < 1024.
-GB_HD GB_INLINE void mul_tw2(float (&re)[32], float (&im)[32], int lane, const float2* tw2) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const float2 w = tw2[lane + 32 * j];
-        const float a = re[j], b = im[j];
-        re[j] = a * w.x - b * w.y;
-        im[j] = a * w.y + b * w.x;
-    }
-}
+// x[n] *= W2048^n (forward odd half) for n = lane + 32 j;  tw2[pidx(j, lane)] = exp(-2 pi i n / 2048), n < 1024.
+GB_HD GB_INLINE void mul_tw2(float (&re)[32], float (&im)[32], int lane, const float2* tw2) { mul_vec(re, im, lane, tw2); }
+
 // Fast magnitude: MUFU.SQRT (sqrt.approx, ~1 ulp) on the device instead of the IEEE sequence with its slow path.
 GB_HD GB_INLINE float gb_sqrt(float x) {
 #if defined(__CUDA_ARCH__)
@@ -112,32 +209,42 @@ GB_HD GB_INLINE float gb_sqrt(float x) {
 GB_HD GB_INLINE void combine_even(const float (&re)[32], const float (&im)[32], int lane, const float2* tw2,
                                   const float2* theirs, float (&xr)[16], float (&xi)[16]) {
 #pragma unroll
-    for (int jj = 0; jj < 16; ++jj) {
-        const float2 o = theirs[jj * 32 + lane];
-        const float2 w = tw2[lane + 32 * jj];
-        xr[jj] = re[jj] + (o.x * w.x + o.y * w.y);
-        xi[jj] = im[jj] + (o.y * w.x - o.x * w.y);
+    for (int p = 0; p < 8; ++p) {
+        float2 o0, o1, w0, w1;
+        ld_pair(theirs + 2 * (p * 32 + lane), o0, o1);
+        ld_pair(tw2 + 2 * (p * 32 + lane), w0, w1);
+        xr[2 * p] = re[2 * p] + (o0.x * w0.x + o0.y * w0.y);
+        xi[2 * p] = im[2 * p] + (o0.y * w0.x - o0.x * w0.y);
+        xr[2 * p + 1] = re[2 * p + 1] + (o1.x * w1.x + o1.y * w1.y);
+        xi[2 * p + 1] = im[2 * p + 1] + (o1.y * w1.x - o1.x * w1.y);
     }
 }
 GB_HD GB_INLINE void combine_odd(const float (&re)[32], const float (&im)[32], int lane, const float2* tw2,
                                  const float2* theirs, float (&xr)[16], float (&xi)[16]) {
 #pragma unroll
-    for (int jj = 0; jj < 16; ++jj) {
-        const float2 e = theirs[jj * 32 + lane];
-        const float2 w = tw2[lane + 32 * (16 + jj)];
-        xr[jj] = e.x + (re[16 + jj] * w.x + im[16 + jj] * w.y);
-        xi[jj] = e.y + (im[16 + jj] * w.x - re[16 + jj] * w.y);
+    for (int p = 0; p < 8; ++p) {
+        float2 e0, e1, w0, w1;
+        ld_pair(theirs + 2 * (p * 32 + lane), e0, e1);
+        ld_pair(tw2 + 2 * ((8 + p) * 32 + lane), w0, w1);
+        const int j = 16 + 2 * p;
+        xr[2 * p] = e0.x + (re[j] * w0.x + im[j] * w0.y);
+        xi[2 * p] = e0.y + (im[j] * w0.x - re[j] * w0.y);
+        xr[2 * p + 1] = e1.x + (re[j + 1] * w1.x + im[j + 1] * w1.y);
+        xi[2 * p + 1] = e1.y + (im[j + 1] * w1.x - re[j + 1] * w1.y);
     }
 }
-// What each warp hands to its partner: the even-bin warp its E[k] for the upper lags, the odd-bin warp its raw
-// O[k] for the lower lags.
+// What each warp hands to its partner (pair-interleaved, [pidx(jj, lane)]): the even-bin warp its E[k] for the upper
+// lags, the odd-bin warp its raw O[k] for the lower lags.
 GB_HD GB_INLINE void exchange_store(const float (&re)[32], const float (&im)[32], int lane, int h, float2* mine) {
     if (h == 0) {
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) mine[jj * 32 + lane] = make_float2(re[16 + jj], im[16 + jj]);
+        for (int p = 0; p < 8; ++p)
+            st_pair(mine + 2 * (p * 32 + lane), make_float2(re[16 + 2 * p], im[16 + 2 * p]),
+                    make_float2(re[17 + 2 * p], im[17 + 2 * p]));
     } else {
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) mine[jj * 32 + lane] = make_float2(re[jj], im[jj]);
+        for (int p = 0; p < 8; ++p)
+            st_pair(mine + 2 * (p * 32 + lane), make_float2(re[2 * p], im[2 * p]), make_float2(re[2 * p + 1], im[2 * p + 1]));
     }
 }
 
@@ -171,16 +278,6 @@ GB_HD GB_INLINE void thread_peak16(const float (&v)[16], int lane, int h, int s,
     out.cnt = c;
     out.sum = 0.0;
     fsum = sm;
-}
-
-GB_HD GB_INLINE void mul_tw2_conj(float (&re)[32], float (&im)[32], int lane, const float2* tw2) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const float2 w = tw2[lane + 32 * j];
-        const float a = re[j], b = im[j];
-        re[j] = a * w.x + b * w.y;
-        im[j] = b * w.x - a * w.y;
-    }
 }
 
 }  // namespace gb

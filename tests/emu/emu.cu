@@ -18,11 +18,11 @@ static void init_tables() {
     for (int k1 = 0; k1 < 32; ++k1)
         for (int l = 0; l < 32; ++l) {
             double a = -2.0 * M_PI * ((l * k1) % 1024) / 1024.0;
-            g_tw1[k1 * 32 + l] = make_float2((float)cos(a), (float)sin(a));
+            g_tw1[pidx(k1, l)] = make_float2((float)cos(a), (float)sin(a));
         }
     for (int n = 0; n < 1024; ++n) {
         double a = -2.0 * M_PI * n / 2048.0;
-        g_tw2[n] = make_float2((float)cos(a), (float)sin(a));
+        g_tw2[zpos(n)] = make_float2((float)cos(a), (float)sin(a));
     }
 }
 
@@ -66,7 +66,7 @@ void emu_replica_spectrum(const uint8_t* chips, float2* crep) {
     for (int g = 0; g < kPad; ++g) {
         double re, im;
         replica_spectrum_bin(chips, g, cs.data(), re, im);
-        crep[(g & 1) * 1024 + (g >> 1)] = make_float2((float)re, (float)im);
+        crep[(g & 1) * 1024 + zpos(g >> 1)] = make_float2((float)re, (float)im);
     }
 }
 
@@ -85,23 +85,38 @@ void emu_cell_profile(const float2* iq, int N, int n_ms, double fs, double doppl
     WarpRegs* w = new WarpRegs;
     WarpRegs* wo = new WarpRegs;
     const double inv_fs = 1.0 / fs;
-    // ---- doppler_spectra ----
+    // ---- doppler_spectra (mirrors k_doppler_spectra<S>: 256 "threads", carrier = coarse x fine table) ----
     for (int i = 0; i < n_ms; ++i) {
+        float2 coarse[64], fine[256];
+        for (int k = 0; k < (N + 255) / 256; ++k) coarse[k] = carrier_at(doppler, (double)(k * 256 + i * N), inv_fs);
+        for (int t = 0; t < 256; ++t) fine[t] = carrier_at(doppler, (double)t, inv_fs);
         for (int n = 0; n < N; ++n) {
-            const double cyc = doppler * ((double)(n + i * N) * inv_fs);
-            ypoly[(size_t)(n % s) * kFft + n / s] = wipeoff(iq[(size_t)i * N + n], cyc);
+            const float2 y = cmul(iq[(size_t)i * N + n], cmul(coarse[n / 256], fine[n % 256]));
+            ypoly[(size_t)(n % s) * kFft + zpos(n / s)] = y;
         }
-        for (int t = 0; t < s; ++t) ypoly[(size_t)t * kFft + 1023] = ypoly[(size_t)t * kFft];
+        for (int t = 0; t < s; ++t) ypoly[(size_t)t * kFft + zpos(kFft - 1)] = ypoly[(size_t)t * kFft + zpos(0)];
+        if (s > 1) {
+            std::vector<float2> znew((size_t)s * kFft);
+            for (int m = 0; m < kChips; ++m) {
+                switch (s) {
+#define EMU_CASE(S) case S: { float2 z[S]; boxcar_column<S>(ypoly.data(), m, z); for (int r = 0; r < S; ++r) znew[(size_t)r * kFft + zpos(m)] = z[r]; } break;
+                    EMU_CASE(2) EMU_CASE(3) EMU_CASE(4) EMU_CASE(5) EMU_CASE(6) EMU_CASE(8) EMU_CASE(10) EMU_CASE(12) EMU_CASE(16)
+#undef EMU_CASE
+                }
+            }
+            for (int t = 0; t < s; ++t)
+                for (int m = 0; m < kChips; ++m) ypoly[(size_t)t * kFft + zpos(m)] = znew[(size_t)t * kFft + zpos(m)];
+        }
+        for (int t = 0; t < s; ++t) ypoly[(size_t)t * kFft + zpos(kFft - 1)] = make_float2(0.f, 0.f);
         for (int r = 0; r < s; ++r)
             for (int half = 0; half < 2; ++half) {
                 for (int lane = 0; lane < 32; ++lane) {
-                    build_z(w->re[lane], w->im[lane], lane, r, s, ypoly.data());
+                    load_vec(w->re[lane], w->im[lane], lane, ypoly.data() + (size_t)r * kFft);
                     if (half) mul_tw2(w->re[lane], w->im[lane], lane, g_tw2.data());
                 }
                 warp_fft1024(*w, false, tile.data());
                 float2* dst = &spec[(((size_t)i * s + r) * 2 + half) * kFft];
-                for (int lane = 0; lane < 32; ++lane)
-                    for (int j = 0; j < 32; ++j) dst[j * 32 + lane] = make_float2(w->re[lane][j], w->im[lane][j]);
+                for (int lane = 0; lane < 32; ++lane) store_vec(w->re[lane], w->im[lane], lane, dst);
             }
     }
     // ---- correlate_cells ----
@@ -116,22 +131,23 @@ void emu_cell_profile(const float2* iq, int N, int n_ms, double fs, double doppl
         for (int it = 0; it < n_iter; ++it) {
             for (int half = 0; half < 2; ++half) {
                 WarpRegs* ww = half ? wo : w;
-                for (int lane = 0; lane < 32; ++lane)
-                    for (int j = 0; j < 32; ++j) {
-                        float2 a = make_float2(0.f, 0.f);
-                        if (kind == 1) {
-                            for (int i = 0; i < n_ms; ++i) {
-                                const float2 v = spec[(((size_t)i * s + r) * 2 + half) * kFft + j * 32 + lane];
-                                a.x += v.x;
-                                a.y += v.y;
+                for (int lane = 0; lane < 32; ++lane) {
+                    if (kind == 1) {
+                        for (int j = 0; j < 32; ++j) ww->re[lane][j] = ww->im[lane][j] = 0.f;
+                        for (int i = 0; i < n_ms; ++i) {
+                            float tr[32], ti[32];
+                            load_vec(tr, ti, lane, &spec[(((size_t)i * s + r) * 2 + half) * kFft]);
+                            for (int j = 0; j < 32; ++j) {
+                                ww->re[lane][j] += tr[j];
+                                ww->im[lane][j] += ti[j];
                             }
-                        } else {
-                            a = spec[(((size_t)it * s + r) * 2 + half) * kFft + j * 32 + lane];
                         }
-                        const float2 y = cmul(a, crep[half * 1024 + j * 32 + lane]);
-                        ww->re[lane][j] = y.x;
-                        ww->im[lane][j] = y.y;
+                        mul_vec(ww->re[lane], ww->im[lane], lane, crep.data() + half * 1024);
+                    } else {
+                        load_mul_vec(ww->re[lane], ww->im[lane], lane, &spec[(((size_t)it * s + r) * 2 + half) * kFft],
+                                     crep.data() + half * 1024);
                     }
+                }
                 warp_fft1024(*ww, true, half ? tileO.data() : tile.data());
                 // (all lanes have finished phase 2 before the tile is reused for the exchange)
                 for (int lane = 0; lane < 32; ++lane)
