@@ -31,19 +31,30 @@ __device__ __forceinline__ int pymod_int(int a, int m) {
     return r < 0 ? r + m : r;
 }
 
+// The float64 loop filters run on one thread; keeping them out of line keeps the per-millisecond instruction
+// footprint of the other warps small (the loop body otherwise overflows the instruction cache).
+__device__ __noinline__ void track_update_device(TrackState* st, float2 E, float2 L, float2 peak, float strength, int key,
+                                                 double t0, double fs, TrackMsRecord* out) {
+    TrackMsRecord rec;
+    track_update(*st, E, L, peak, strength, key, t0, fs, rec);
+    *out = rec;
+}
+
+template <int S>
 __global__ void __launch_bounds__(kTrackThreads, 1) k_track_channels(const TrackArgs a) {
     extern __shared__ __align__(16) float2 smem[];
-    const int n_fft_warps = 2 * a.s;
-    float2* iqbuf = smem;                                    // [2][N]
-    float2* ypoly = iqbuf + 2 * a.N;                         // [s][1024]
-    float2* crep_s = ypoly + static_cast<size_t>(a.s) * kFft;  // [2][1024]
+    constexpr int n_fft_warps = 2 * S;
+    float2* iqbuf = smem;                 // [2][N]
+    float2* ypoly = iqbuf + 2 * a.N;      // [S][1024]
+    float2* crep_s = ypoly + S * kFft;    // [2][1024]
     float2* tw1_s = crep_s + 2 * kFft;
     float2* tw2_s = tw1_s + kFft;
     float2* tiles = tw2_s + kFft;                            // [2s][kTileF2]
     TrackState* st = reinterpret_cast<TrackState*>(tiles + static_cast<size_t>(n_fft_warps) * kTileF2);
     TrackPartial* partial = reinterpret_cast<TrackPartial*>(st + 1);  // [8]
     float2* el = reinterpret_cast<float2*>(partial + 8);              // [2] early, late
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(el + 2);
+    float2* coarse = el + 2;                                          // [16] carrier at samples 0, 256, ... (+ phase)
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(coarse + 16);
 
     const int ch = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -103,29 +114,40 @@ __global__ void __launch_bounds__(kTrackThreads, 1) k_track_channels(const Track
         const int pm = pymod_int(p, a.N);
         const int kE = pymod_int(p - 1, a.N), kL = pymod_int(p + 1, a.N);
 
-        // ---- carrier wipe-off (tracker.py:278-281), polyphase de-interleave ----
-        const float2* buf = iqbuf + (k & 1) * a.N;
-        for (int n = tid; n < a.N; n += kTrackThreads) {
-            const double cyc = f * (static_cast<double>(n) * a.inv_fs + t0) + phi_cycles;
-            ypoly[(n % a.s) * kFft + n / a.s] = wipeoff(buf[n], cyc);
-        }
+        // ---- carrier wipe-off (tracker.py:278-281): exp(-j(2 pi f (n/fs + t0) + phi)) = coarse[n/256] * fine[n%256],
+        //      each factor from a float64-reduced phase; polyphase de-interleave ----
+        if (tid < (a.N + kTrackThreads - 1) / kTrackThreads)
+            coarse[tid] = wipeoff(make_float2(1.f, 0.f), f * (static_cast<double>(tid * kTrackThreads) * a.inv_fs + t0) + phi_cycles);
+        const float2 fine = carrier_at(f, static_cast<double>(tid), a.inv_fs);
         __syncthreads();
-        if (tid < a.s) ypoly[tid * kFft + (kFft - 1)] = ypoly[tid * kFft];
+        const float2* buf = iqbuf + (k & 1) * a.N;
+        for (int kk = 0, n = tid; n < a.N; ++kk, n += kTrackThreads)
+            ypoly[(n % S) * kFft + n / S] = cmul(buf[n], cmul(coarse[kk], fine));
+        __syncthreads();
+        if (tid < S) ypoly[tid * kFft + (kFft - 1)] = ypoly[tid * kFft];
         __syncthreads();
 
         if (warp < n_fft_warps) {
             float re[32], im[32];
-            build_z(re, im, lane, r, a.s, ypoly);
-            if (h) mul_tw2(re, im, lane, tw2_s);
-            wfft_phase1(re, im, lane, tw1_s, tile);
-            __syncwarp();
-            wfft_phase2(re, im, lane, tile);
-            __syncwarp();
-            mul_vec(re, im, lane, crep_s + h * kFft);
-            wfft_phase1(im, re, lane, tw1_s, tile);
-            __syncwarp();
-            wfft_phase2(im, re, lane, tile);
-            __syncwarp();
+            // forward transform, spectrum product, inverse transform (= conj, forward, conj): one copy of the
+            // warp-FFT code serves both passes.
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                if (pass == 0) {
+                    build_z(re, im, lane, r, S, ypoly);
+                    if (h) mul_tw2(re, im, lane, tw2_s);
+                } else {
+                    mul_vec(re, im, lane, crep_s + h * kFft);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) im[j] = -im[j];
+                }
+                wfft_phase1(re, im, lane, tw1_s, tile);
+                __syncwarp();
+                wfft_phase2(re, im, lane, tile);
+                __syncwarp();
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) im[j] = -im[j];
             exchange_store(re, im, lane, h, tile);
             pair_barrier(r);
             float xr[16], xi[16];
@@ -139,7 +161,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) k_track_channels(const Track
             for (int jj = 0; jj < 16; ++jj) {
                 const int q = lane + 32 * (16 * h + jj);
                 if (q < kChips) {
-                    const int n = a.s * q + r;
+                    const int n = S * q + r;
                     const float v = gb_sqrt(xr[jj] * xr[jj] + xi[jj] * xi[jj]);
                     int kk = n - pm;
                     kk = kk < 0 ? kk + a.N : kk;
@@ -201,9 +223,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) k_track_channels(const Track
             }
             const double m = static_cast<double>(mx);
             const float strength = static_cast<float>(m / ((sum - cnt * m) / (a.N - cnt)));  // utils.py:111-116
-            TrackMsRecord rec;
-            track_update(*st, el[0], el[1], make_float2(pre, pim), strength, key, t0, a.fs, rec);
-            out[k] = rec;
+            track_update_device(st, el[0], el[1], make_float2(pre, pim), strength, key, t0, a.fs, &out[k]);
         }
         // the __syncthreads at the top of the next millisecond publishes st / frees el, partial
     }
@@ -218,15 +238,20 @@ __global__ void __launch_bounds__(kTrackThreads, 1) k_track_channels(const Track
 size_t track_smem_bytes(int N, int s) {
     return (2 * static_cast<size_t>(N) + static_cast<size_t>(s) * kFft + 4 * kFft + 2 * static_cast<size_t>(s) * kTileF2) *
                sizeof(float2) +
-           sizeof(TrackState) + 8 * sizeof(TrackPartial) + 2 * sizeof(float2) + 16;
+           sizeof(TrackState) + 8 * sizeof(TrackPartial) + (2 + 16) * sizeof(float2) + 16;
 }
 
 cudaError_t configure_track_kernel() {
-    return cudaFuncSetAttribute(k_track_channels, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_track_channels<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_track_channels<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
 cudaError_t launch_track_channels(const TrackArgs& a, cudaStream_t st) {
-    k_track_channels<<<a.n_channels, kTrackThreads, track_smem_bytes(a.N, a.s), st>>>(a);
+    const size_t sm = track_smem_bytes(a.N, a.s);
+    if (a.s == 2) k_track_channels<2><<<a.n_channels, kTrackThreads, sm, st>>>(a);
+    else if (a.s == 4) k_track_channels<4><<<a.n_channels, kTrackThreads, sm, st>>>(a);
+    else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
 

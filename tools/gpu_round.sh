@@ -4,8 +4,6 @@ TAG=${1:-x}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
 timeout 900 python tools/bench_configs.py 2>&1 | tee gpurun_out/configs_${TAG}.jsonl | cut -c1-600
-echo "--- NP=10"
-GB200_NP=10 timeout 600 python tools/bench_configs.py --quick 2>&1 | tee gpurun_out/configs_${TAG}_np10.jsonl | cut -c1-400
 if [ "${2:-}" = "profile" ]; then
   bash tools/gpu_profile.sh ${TAG}
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_track_channels -s 1 -c 1 \
