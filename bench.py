@@ -354,8 +354,7 @@ def main() -> None:
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        if args.steps > 20:
-            args.steps = 20  # bounded: a CPU step is ~1e4 x slower than a GPU step
+        args.steps = min(args.steps, 2000)  # bounded: ~13 ms per CPU step on 32 cores
         run_reference(args, rank, world)
     else:
         run_ours(args, rank, local_rank, world)
