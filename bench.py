@@ -262,11 +262,14 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     eng.enable_kernel_timing(False)
 
     # ---- end to end through the public host API ----
+    rec_pinned = torch.empty(B * n_cells * 32, dtype=torch.uint8).pin_memory()
+    rec_host = rec_pinned.numpy().view(_native.RECORD_DTYPE).reshape(B, N_PRN, len(DOPPLERS))
+
     def e2e_step(k: int) -> None:
+        # host IQ (pinned) -> device, full grid, per-cell records back into a pinned host array
         slot = k % n_slots
         eng.upload_iq_ptr(ring_host.data_ptr() + slot * B * block_bytes, B * N)
-        out = eng.acquire_grid(B, N_MS, prn, dop, _native.NON_COHERENT)
-        e2e_step.last = out
+        e2e_step.last = eng.acquire_grid(B, N_MS, prn, dop, _native.NON_COHERENT, out=rec_host)
 
     for k in range(3):
         e2e_step(k)

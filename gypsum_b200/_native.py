@@ -154,10 +154,16 @@ class Engine:
         self._check(self._lib.gb200_bind_iq_device(self._h, _P(device_ptr), n_samples), "gb200_bind_iq_device")
 
     # -- the hot path --------------------------------------------------------------------------------------
-    def acquire_grid(self, n_blocks: int, ms_per_block: int, prn_idx, doppler_hz, kind: int = NON_COHERENT) -> np.ndarray:
+    def acquire_grid(self, n_blocks: int, ms_per_block: int, prn_idx, doppler_hz, kind: int = NON_COHERENT,
+                     out: np.ndarray | None = None) -> np.ndarray:
+        """out: optional preallocated RECORD_DTYPE array [n_blocks, n_prn, n_doppler]; if it lives in pinned memory
+        (e.g. a view of a torch pinned tensor) the records are DMA'd straight into it."""
         prn = np.ascontiguousarray(prn_idx, dtype=np.int32)
         dop = np.ascontiguousarray(doppler_hz, dtype=np.float64)
-        out = np.empty((n_blocks, prn.size, dop.size), dtype=RECORD_DTYPE)
+        if out is None:
+            out = np.empty((n_blocks, prn.size, dop.size), dtype=RECORD_DTYPE)
+        elif out.dtype != RECORD_DTYPE or out.shape != (n_blocks, prn.size, dop.size) or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("out must be a C-contiguous RECORD_DTYPE array of shape [n_blocks, n_prn, n_doppler]")
         self._check(
             self._lib.gb200_acquire_grid(self._h, n_blocks, ms_per_block, _ptr(prn), prn.size, _ptr(dop), dop.size, kind,
                                          _ptr(out)),

@@ -97,6 +97,30 @@ struct gb200_engine {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[2];
     size_t ev_used[2] = {0, 0};
     std::string err;
+
+    ~gb200_engine() {
+        tw1.release();
+        tw2.release();
+        crep.release();
+        iq_own.release();
+        spec.release();
+        chips.release();
+        d_doppler.release();
+        d_ints.release();
+        d_records.release();
+        d_profile.release();
+        h_iq.release();
+        h_records.release();
+        h_ints.release();
+        h_doubles.release();
+        h_profile.release();
+        for (auto& pool : ev)
+            for (auto& pr : pool) {
+                cudaEventDestroy(pr.first);
+                cudaEventDestroy(pr.second);
+            }
+        if (own_stream) cudaStreamDestroy(own_stream);
+    }
 };
 
 struct gb200_tracker {
@@ -391,7 +415,20 @@ int run_cells(gb200_engine* e, int n_cells, const int32_t* prn_idx, const double
     return GB200_OK;
 }
 
+bool is_pinned_host(const void* p) {
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    return pinned;
+}
+
+// Records to the caller: straight DMA when the caller's buffer is pinned, else through the engine's pinned staging.
 int fetch_records(gb200_engine* e, size_t n, gb200_cell_record* out_host) {
+    if (is_pinned_host(out_host)) {
+        GB_CUDA(e, cudaMemcpyAsync(out_host, e->d_records.p, n * sizeof(CellRecord), cudaMemcpyDeviceToHost, e->stream));
+        GB_CUDA(e, cudaStreamSynchronize(e->stream));
+        return GB200_OK;
+    }
     GB_CUDA(e, e->h_records.ensure(n));
     GB_CUDA(e, cudaMemcpyAsync(e->h_records.p, e->d_records.p, n * sizeof(CellRecord), cudaMemcpyDeviceToHost, e->stream));
     GB_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -466,28 +503,7 @@ int gb200_destroy(gb200_engine* e) {
     if (!e) return GB200_OK;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
-    e->tw1.release();
-    e->tw2.release();
-    e->crep.release();
-    e->iq_own.release();
-    e->spec.release();
-    e->chips.release();
-    e->d_doppler.release();
-    e->d_ints.release();
-    e->d_records.release();
-    e->d_profile.release();
-    e->h_iq.release();
-    e->h_records.release();
-    e->h_ints.release();
-    e->h_doubles.release();
-    e->h_profile.release();
-    for (auto& pool : e->ev)
-        for (auto& pr : pool) {
-            cudaEventDestroy(pr.first);
-            cudaEventDestroy(pr.second);
-        }
-    if (e->own_stream) cudaStreamDestroy(e->own_stream);
-    delete e;
+    delete e;  // ~gb200_engine releases every device / pinned allocation, the events and the stream
     return GB200_OK;
 }
 
@@ -522,9 +538,7 @@ int gb200_upload_iq(gb200_engine* e, const float* iq_host, int64_t n_samples) {
     GB_CUDA(e, cudaSetDevice(e->device));
     GB_CUDA(e, e->iq_own.ensure(static_cast<size_t>(std::max<int64_t>(n_samples, 1))));
     const void* src = iq_host;
-    cudaPointerAttributes attr;
-    const bool pinned = cudaPointerGetAttributes(&attr, iq_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-    cudaGetLastError();
+    const bool pinned = is_pinned_host(iq_host);
     if (!pinned) {
         GB_CUDA(e, cudaStreamSynchronize(e->stream));  // staging buffer may still be in flight
         GB_CUDA(e, e->h_iq.ensure(static_cast<size_t>(std::max<int64_t>(n_samples, 1))));
