@@ -25,6 +25,9 @@ TRACK_DTYPE = np.dtype(
      ("peak_offset", "<i4"), ("reserved0", "<i4"), ("reserved1", "<i4")]
 )
 assert TRACK_DTYPE.itemsize == 96
+ACQ_DTYPE = np.dtype([("doppler", "<f8"), ("strength", "<f8"), ("probe_re", "<f4"), ("probe_im", "<f4"),
+                      ("code_phase", "<i4"), ("reserved", "<i4")])
+assert ACQ_DTYPE.itemsize == 32
 
 # every symbol include/gypsum_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
@@ -40,6 +43,7 @@ SYMBOLS = {
     "gb200_acquire_grid": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P]),
     "gb200_acquire_grid_device": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P]),
     "gb200_acquire_cells": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "gb200_detect": (C.c_int, [_P, C.c_int, _P, C.c_int, _P]),
     "gb200_correlation_profile": (C.c_int, [_P, C.c_int, C.c_double, C.c_int, C.c_int, _P]),
     "gb200_tracker_create": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.POINTER(_P)]),
     "gb200_tracker_destroy": (C.c_int, [_P]),
@@ -191,6 +195,13 @@ class Engine:
                                           n_ms, kind, _ptr(out)),
             "gb200_acquire_cells",
         )
+        return out
+
+    def detect(self, prn_idx, n_ms: int) -> np.ndarray:
+        """acquisition.py:70-152 for every listed replica row, all ten passes + the coherent pass on the device."""
+        prn = np.ascontiguousarray(prn_idx, dtype=np.int32)
+        out = np.empty(prn.size, dtype=ACQ_DTYPE)
+        self._check(self._lib.gb200_detect(self._h, prn.size, _ptr(prn), int(n_ms), _ptr(out)), "gb200_detect")
         return out
 
     def correlation_profile(self, prn_idx: int, doppler_hz: float, n_ms: int, kind: int) -> np.ndarray:

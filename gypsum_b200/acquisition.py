@@ -100,7 +100,24 @@ class GpsSatelliteDetector:
         return out
 
     def _acquire_many(self, satellite_ids, antenna_data, stream_attributes) -> list[SatelliteAcquisitionAttemptResult]:
-        """acquisition.py:70-152 for a batch of satellites advancing through the passes in lock-step."""
+        """acquisition.py:70-152 for a batch of satellites: one gb200_detect call -- the ten refinement passes, the
+        bin selection between them and the final coherent integration all run on the device."""
+        if not satellite_ids:
+            return []
+        eng, prn_idx, n, n_ms = self._prepare(satellite_ids, antenna_data, stream_attributes)
+        rec = eng.detect(prn_idx, n_ms)
+        phase = np.angle(rec["probe_re"].astype(np.float64) + 1j * rec["probe_im"].astype(np.float64))
+        return [
+            SatelliteAcquisitionAttemptResult(
+                satellite_id=sid, doppler_shift=int(rec["doppler"][i]), carrier_wave_phase_shift=phase[i],
+                prn_phase_shift=int(rec["code_phase"][i]), correlation_strength=float(rec["strength"][i]),
+            )
+            for i, sid in enumerate(satellite_ids)
+        ]
+
+    def _acquire_many_stepwise(self, satellite_ids, antenna_data, stream_attributes) -> list[SatelliteAcquisitionAttemptResult]:
+        """The same search driven pass by pass from the host (one gb200_acquire_cells call per pass); kept as the
+        cross-check of the on-device driver and for callers that want to observe the passes."""
         if not satellite_ids:
             return []
         eng, prn_idx, n, n_ms = self._prepare(satellite_ids, antenna_data, stream_attributes)

@@ -79,6 +79,14 @@ struct gb200_engine {
     DevBuf<int> d_ints;
     DevBuf<CellRecord> d_records;
     DevBuf<float> d_profile;
+    // on-device refinement (gb200_detect)
+    DevBuf<RefineState> r_state;
+    DevBuf<double> r_doppler;
+    DevBuf<CellRecord> r_records;
+    DevBuf<int> r_ints;
+    DevBuf<RefineResult> r_results;
+    PinnedBuf<int> rh_ints;
+    PinnedBuf<RefineResult> rh_results;
     PinnedBuf<float2> h_iq;
     PinnedBuf<CellRecord> h_records;
     PinnedBuf<int> h_ints;
@@ -109,6 +117,13 @@ struct gb200_engine {
         d_ints.release();
         d_records.release();
         d_profile.release();
+        r_state.release();
+        r_doppler.release();
+        r_records.release();
+        r_ints.release();
+        r_results.release();
+        rh_ints.release();
+        rh_results.release();
         h_iq.release();
         h_records.release();
         h_ints.release();
@@ -632,6 +647,168 @@ int gb200_kernel_timing(gb200_engine* e, int which, double* total_ms, int64_t* l
     }
     *total_ms = t;
     *launches = static_cast<int64_t>(e->ev_used[which]);
+    return GB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// on-device acquisition search (acquisition.py:70-152)
+// ---------------------------------------------------------------------------------------------------------
+static_assert(sizeof(gb200_acquisition_result) == sizeof(RefineResult), "ABI acquisition result must match");
+
+int gb200_detect(gb200_engine* e, int n_sv, const int32_t* prn_idx, int n_ms, gb200_acquisition_result* out_host) {
+    if (!e) return GB200_EINVAL;
+    if (!out_host) GB_FAIL(e, GB200_EINVAL, "null output");
+    GB_CUDA(e, cudaSetDevice(e->device));
+    int rc = check_common(e, n_ms, GB200_NON_COHERENT);
+    if (rc) return rc;
+    if (n_sv < 1 || !prn_idx) GB_FAIL(e, GB200_EINVAL, "no satellites to search for");
+    if (static_cast<int64_t>(n_ms) * e->N > e->iq_samples)
+        GB_FAIL(e, GB200_EINVAL, "need %lld samples, %lld loaded", static_cast<long long>(n_ms) * e->N,
+                static_cast<long long>(e->iq_samples));
+    for (int i = 0; i < n_sv; ++i)
+        if (prn_idx[i] < 0 || prn_idx[i] >= e->n_prn) GB_FAIL(e, GB200_EINVAL, "prn index %d out of range", prn_idx[i]);
+
+    const int MAXB = kRefineMaxBins;
+    const int n_cells = n_sv * MAXB;
+    const int rsplit = pick_rsplit(e, n_cells);
+    const int cpg = e->np / rsplit;
+    const int gps = (MAXB + cpg - 1) / cpg;  // groups per satellite
+    const size_t unit = unit_floats2(e, n_ms);
+    int sv_per_chunk = static_cast<int>(std::max<size_t>(1, e->spec_budget_bytes / (unit * sizeof(float2) * MAXB)));
+    sv_per_chunk = std::min(sv_per_chunk, n_sv);
+
+    // ---- static plan: cell c = sv*MAXB + b ----
+    // ints: [cell_u n_cells][cell_out n_cells][grp_first][grp_count][grp_prn] (n_sv*gps each)
+    //       then the coherent pass: [ccell_u n_sv][ccell_out n_sv][cgrp_first][cgrp_count][cgrp_prn] (n_sv each), [probe n_sv]
+    const int ng = n_sv * gps;
+    const size_t n_ints = static_cast<size_t>(2) * n_cells + 3 * ng + 6 * n_sv;
+    GB_CUDA(e, cudaStreamSynchronize(e->stream));
+    GB_CUDA(e, e->r_ints.ensure(n_ints));
+    GB_CUDA(e, e->rh_ints.ensure(n_ints));
+    int* hi = e->rh_ints.p;
+    int* cell_u = hi;
+    int* cell_out = cell_u + n_cells;
+    int* g_first = cell_out + n_cells;
+    int* g_count = g_first + ng;
+    int* g_prn = g_count + ng;
+    int* cc_u = g_prn + ng;
+    int* cc_out = cc_u + n_sv;
+    int* cg_first = cc_out + n_sv;
+    int* cg_count = cg_first + n_sv;
+    int* cg_prn = cg_count + n_sv;
+    for (int sv = 0; sv < n_sv; ++sv) {
+        for (int b = 0; b < MAXB; ++b) {
+            cell_u[sv * MAXB + b] = (sv % sv_per_chunk) * MAXB + b;
+            cell_out[sv * MAXB + b] = sv * MAXB + b;
+        }
+        for (int g = 0; g < gps; ++g) {
+            g_first[sv * gps + g] = sv * MAXB + g * cpg;
+            g_count[sv * gps + g] = std::min(cpg, MAXB - g * cpg);
+            g_prn[sv * gps + g] = prn_idx[sv];
+        }
+        cc_u[sv] = sv;
+        cc_out[sv] = sv;
+        cg_first[sv] = sv;
+        cg_count[sv] = 1;
+        cg_prn[sv] = prn_idx[sv];
+    }
+    int* di = e->r_ints.p;
+    GB_CUDA(e, cudaMemcpyAsync(di, hi, sizeof(int) * (n_ints - n_sv), cudaMemcpyHostToDevice, e->stream));
+    int* d_probe = di + (n_ints - n_sv);
+
+    GB_CUDA(e, e->r_state.ensure(n_sv));
+    GB_CUDA(e, e->r_doppler.ensure(static_cast<size_t>(n_cells) + n_sv));
+    GB_CUDA(e, e->r_records.ensure(static_cast<size_t>(n_cells) + n_sv));
+    GB_CUDA(e, e->r_results.ensure(n_sv));
+    GB_CUDA(e, e->rh_results.ensure(n_sv));
+    GB_CUDA(e, e->spec.ensure(unit * std::max(sv_per_chunk * MAXB, n_sv)));
+    double* d_coh_doppler = e->r_doppler.p + n_cells;
+    CellRecord* d_coh_records = e->r_records.p + n_cells;
+
+    auto spectra = [&](const double* dop, int n_units) -> cudaError_t {
+        SpectraArgs sa{};
+        sa.iq = e->iq;
+        sa.doppler = dop;
+        sa.spec = e->spec.p;
+        sa.tw1 = e->tw1.p;
+        sa.tw2 = e->tw2.p;
+        sa.block_stride = 0;
+        sa.inv_fs = 1.0 / static_cast<double>(e->fs);
+        sa.N = e->N;
+        sa.s = e->s;
+        sa.M = n_ms;
+        sa.n_doppler = n_units;
+        sa.n_units = n_units;
+        TimedLaunch tl(e, 0);
+        e->launches++;
+        return launch_doppler_spectra(sa, e->stream);
+    };
+    CorrelateArgs base{};
+    base.spec = e->spec.p;
+    base.crep = e->crep.p;
+    base.tw1 = e->tw1.p;
+    base.tw2 = e->tw2.p;
+    base.profile = nullptr;
+    base.N = e->N;
+    base.s = e->s;
+    base.M = n_ms;
+    base.rsplit = rsplit;
+    base.grid_mode = 0;
+
+    GB_CUDA(e, launch_refine_init(n_sv, e->r_state.p, e->stream));
+    e->launches++;
+    for (double spread = 7000.0; spread >= 10.0; spread /= 2.0) {  // acquisition.py:78-89
+        GB_CUDA(e, launch_refine_plan(n_sv, spread, e->r_state.p, e->r_doppler.p, e->stream));
+        e->launches++;
+        for (int sv0 = 0; sv0 < n_sv; sv0 += sv_per_chunk) {
+            const int nsv = std::min(sv_per_chunk, n_sv - sv0);
+            GB_CUDA(e, spectra(e->r_doppler.p + static_cast<size_t>(sv0) * MAXB, nsv * MAXB));
+            CorrelateArgs ca = base;
+            ca.records = e->r_records.p;
+            ca.kind = GB200_NON_COHERENT;
+            ca.n_groups = nsv * gps;
+            ca.cell_u = di;
+            ca.cell_out = di + n_cells;
+            ca.grp_first = di + 2 * n_cells + sv0 * gps;
+            ca.grp_count = di + 2 * n_cells + ng + sv0 * gps;
+            ca.grp_prn = di + 2 * n_cells + 2 * ng + sv0 * gps;
+            ca.cell_probe = nullptr;
+            ca.cell_gate = e->r_doppler.p;
+            {
+                TimedLaunch tl(e, 1);
+                GB_CUDA(e, launch_correlate_cells(ca, e->np, std::min(ca.n_groups, e->num_sms), e->stream));
+            }
+            e->launches++;
+        }
+        GB_CUDA(e, launch_refine_select(n_sv, e->N, e->r_records.p, e->r_doppler.p, e->r_state.p, e->stream));
+        e->launches++;
+    }
+    // coherent integration at the kept Doppler (acquisition.py:120-136)
+    GB_CUDA(e, launch_refine_coherent_plan(n_sv, e->r_state.p, d_coh_doppler, d_probe, e->stream));
+    e->launches++;
+    GB_CUDA(e, spectra(d_coh_doppler, n_sv));
+    {
+        const int* cbase = di + 2 * n_cells + 3 * ng;
+        CorrelateArgs ca = base;
+        ca.records = d_coh_records;
+        ca.kind = GB200_COHERENT;
+        ca.n_groups = n_sv;
+        ca.cell_u = cbase;
+        ca.cell_out = cbase + n_sv;
+        ca.grp_first = cbase + 2 * n_sv;
+        ca.grp_count = cbase + 3 * n_sv;
+        ca.grp_prn = cbase + 4 * n_sv;
+        ca.cell_probe = d_probe;
+        ca.cell_gate = nullptr;
+        TimedLaunch tl(e, 1);
+        GB_CUDA(e, launch_correlate_cells(ca, e->np, std::min(n_sv, e->num_sms), e->stream));
+        e->launches++;
+    }
+    GB_CUDA(e, launch_refine_finalize(n_sv, e->r_state.p, d_coh_records, e->r_results.p, e->stream));
+    e->launches++;
+    GB_CUDA(e, cudaMemcpyAsync(e->rh_results.p, e->r_results.p, sizeof(RefineResult) * n_sv, cudaMemcpyDeviceToHost, e->stream));
+    GB_CUDA(e, cudaStreamSynchronize(e->stream));
+    memcpy(out_host, e->rh_results.p, sizeof(RefineResult) * n_sv);
     return GB200_OK;
 }
 

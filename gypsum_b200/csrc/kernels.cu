@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(kSpecThreads) k_doppler_spectra(const SpectraA
     const int unit = blockIdx.x / a.M, i = blockIdx.x % a.M;
     const int b = unit / a.n_doppler, d = unit % a.n_doppler;
     const double f = a.doppler[d];
+    if (isnan(f)) return;  // slot switched off by the on-device search planner
     const float2* __restrict__ src = a.iq + static_cast<size_t>(b) * a.block_stride + static_cast<size_t>(i) * a.N;
     const int tid = threadIdx.x;
 
@@ -217,7 +218,8 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
                 out = a.cell_out[c];
             }
         }
-        const bool active = my_cell < n_cells;
+        bool active = my_cell < n_cells;
+        if (active && a.cell_gate) active = !isnan(a.cell_gate[out]);
 
         // ---- stage conj(FFT(replica)) of this PRN: TMA bulk copy into shared memory ----
         if (prn != cur_prn) {
@@ -368,6 +370,106 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
         if (a.rsplit != 1) __syncthreads();  // partial[] is free again
         // rsplit == 1: the next write to partial[] comes after at least two more pair barriers
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// On-device Doppler refinement: the control flow of acquisition.py:70-152 without host round trips.  The
+// correlation work of every pass still runs in doppler_spectra / correlate_cells; these kernels only plan the
+// next pass's bins and apply the reference's selection rules.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_refine_init(int n_sv, RefineState* st) {
+    const int sv = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sv >= n_sv) return;
+    st[sv].center = 0.0;  // acquisition.py:77
+    st[sv].kept_doppler = 0.0;
+    st[sv].kept_strength = 0.0;
+    st[sv].kept_index = 0;
+    st[sv].have_kept = 0;
+}
+
+// acquisition.py:163-167: range(int(c - s), int(c + s), int(s / 10)); int() truncates toward zero.
+__global__ void k_refine_plan(int n_sv, double spread, const RefineState* st, double* doppler) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_sv * kRefineMaxBins) return;
+    const int sv = t / kRefineMaxBins, b = t % kRefineMaxBins;
+    const double c = st[sv].center;
+    const long long lo = static_cast<long long>(c - spread), hi = static_cast<long long>(c + spread);
+    const long long step = static_cast<long long>(spread / 10.0);
+    const long long v = lo + b * step;
+    doppler[t] = v < hi ? static_cast<double>(v) : nan("");
+}
+
+// acquisition.py:179-189 (first bin with the largest profile maximum, its argmax and strength) and :89-101
+// (re-centre on this pass's bin; keep the pass with the strictly greatest strength).
+__global__ void k_refine_select(int n_sv, int N, const CellRecord* rec, const double* doppler, RefineState* st) {
+    const int sv = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sv >= n_sv) return;
+    int best = -1;
+    float best_peak = 0.f;
+    for (int b = 0; b < kRefineMaxBins; ++b) {
+        const int c = sv * kRefineMaxBins + b;
+        if (isnan(doppler[c])) continue;
+        if (best < 0 || rec[c].peak > best_peak) {
+            best = b;
+            best_peak = rec[c].peak;
+        }
+    }
+    if (best < 0) return;
+    const CellRecord r = rec[sv * kRefineMaxBins + best];
+    const double peak = static_cast<double>(r.peak);
+    const double strength = peak / ((r.sum - r.count * peak) / (N - r.count));  // utils.py:111-116
+    RefineState s = st[sv];
+    s.center = doppler[sv * kRefineMaxBins + best];
+    if (!s.have_kept || strength > s.kept_strength) {
+        s.have_kept = 1;
+        s.kept_strength = strength;
+        s.kept_doppler = s.center;
+        s.kept_index = r.argmax;
+    }
+    st[sv] = s;
+}
+
+// acquisition.py:120-136: one coherent integration per satellite at the kept Doppler, probed at the kept index.
+__global__ void k_refine_coherent_plan(int n_sv, const RefineState* st, double* doppler, int* probe) {
+    const int sv = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sv >= n_sv) return;
+    doppler[sv] = st[sv].kept_doppler;
+    probe[sv] = st[sv].kept_index;
+}
+
+__global__ void k_refine_finalize(int n_sv, const RefineState* st, const CellRecord* rec, RefineResult* out) {
+    const int sv = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sv >= n_sv) return;
+    RefineResult r;
+    r.doppler = st[sv].kept_doppler;
+    r.strength = st[sv].kept_strength;
+    r.probe_re = rec[sv].probe_re;
+    r.probe_im = rec[sv].probe_im;
+    r.code_phase = st[sv].kept_index;
+    r.pad_ = 0;
+    out[sv] = r;
+}
+
+cudaError_t launch_refine_init(int n_sv, RefineState* st, cudaStream_t s) {
+    k_refine_init<<<(n_sv + 63) / 64, 64, 0, s>>>(n_sv, st);
+    return cudaGetLastError();
+}
+cudaError_t launch_refine_plan(int n_sv, double spread, const RefineState* st, double* doppler, cudaStream_t s) {
+    const int n = n_sv * kRefineMaxBins;
+    k_refine_plan<<<(n + 127) / 128, 128, 0, s>>>(n_sv, spread, st, doppler);
+    return cudaGetLastError();
+}
+cudaError_t launch_refine_select(int n_sv, int N, const CellRecord* rec, const double* doppler, RefineState* st, cudaStream_t s) {
+    k_refine_select<<<(n_sv + 63) / 64, 64, 0, s>>>(n_sv, N, rec, doppler, st);
+    return cudaGetLastError();
+}
+cudaError_t launch_refine_coherent_plan(int n_sv, const RefineState* st, double* doppler, int* probe, cudaStream_t s) {
+    k_refine_coherent_plan<<<(n_sv + 63) / 64, 64, 0, s>>>(n_sv, st, doppler, probe);
+    return cudaGetLastError();
+}
+cudaError_t launch_refine_finalize(int n_sv, const RefineState* st, const CellRecord* rec, RefineResult* out, cudaStream_t s) {
+    k_refine_finalize<<<(n_sv + 63) / 64, 64, 0, s>>>(n_sv, st, rec, out);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------------

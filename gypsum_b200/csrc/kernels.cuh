@@ -41,7 +41,30 @@ struct CorrelateArgs {
     const int* cell_u;      // spectrum unit of each sorted cell
     const int* cell_out;    // where its record goes
     const int* cell_probe;  // coherent probe index or -1 (both modes, indexed by output slot; may be null)
+    const double* cell_gate;  // optional, indexed by output slot: NaN = this cell is switched off (device-planned lists)
 };
+
+// On-device Doppler refinement (reference acquisition.py:70-152): per-satellite search state and result.
+constexpr int kRefineMaxBins = 32;  // acquisition.py:163-167 yields 20..28 bins per pass
+struct RefineState {
+    double center;         // center_doppler_shift_estimation
+    double kept_doppler;   // best_..._across_all_search_space.doppler_shift
+    double kept_strength;  // .correlation_strength
+    int kept_index;        // .sample_offset_of_correlation_peak
+    int have_kept;
+};
+struct RefineResult {  // 32 bytes, mirrored by gb200_acquisition_result
+    double doppler;
+    double strength;
+    float probe_re, probe_im;  // coherent profile value at the kept peak index
+    int code_phase;
+    int pad_;
+};
+cudaError_t launch_refine_plan(int n_sv, double spread, const RefineState* st, double* doppler, cudaStream_t s);
+cudaError_t launch_refine_select(int n_sv, int N, const CellRecord* rec, const double* doppler, RefineState* st, cudaStream_t s);
+cudaError_t launch_refine_coherent_plan(int n_sv, const RefineState* st, double* doppler, int* probe, cudaStream_t s);
+cudaError_t launch_refine_finalize(int n_sv, const RefineState* st, const CellRecord* rec, RefineResult* out, cudaStream_t s);
+cudaError_t launch_refine_init(int n_sv, RefineState* st, cudaStream_t s);
 
 // track_channels: one persistent CTA per channel.
 struct TrackArgs {

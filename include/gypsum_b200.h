@@ -84,6 +84,20 @@ int gb200_acquire_grid_device(gb200_engine* e, int n_blocks, int ms_per_block, c
 int gb200_acquire_cells(gb200_engine* e, int n_cells, const int32_t* prn_idx, const double* doppler_hz,
                         const int32_t* probe_idx, int n_ms, int integration_type, gb200_cell_record* out_host);
 
+/* acquisition.py:70-152 for a batch of satellites, entirely on the device: the ten refinement passes
+ * (spread 7000 Hz halved while >= 10, bins range(int(c-s), int(c+s), int(s/10)), first bin with the largest
+ * profile maximum, kept result = strictly greatest strength), then one coherent integration at the kept Doppler.
+ * No host round trip between passes.  out[i] belongs to prn_idx[i].                                    */
+typedef struct gb200_acquisition_result {
+    double doppler_hz;  /* SatelliteAcquisitionAttemptResult.doppler_shift        (acquisition.py:120)       */
+    double strength;    /* .correlation_strength                                   (acquisition.py:138)       */
+    float probe_re;     /* coherent profile at the kept peak index; np.angle of it */
+    float probe_im;     /*   is .carrier_wave_phase_shift                          (acquisition.py:136)       */
+    int32_t code_phase; /* .prn_phase_shift                                        (acquisition.py:137)       */
+    int32_t reserved;
+} gb200_acquisition_result;
+int gb200_detect(gb200_engine* e, int n_sv, const int32_t* prn_idx, int n_ms, gb200_acquisition_result* out_host);
+
 /* utils.py:77-108 in full: the N-value profile of one cell.  out_host holds N floats (non-coherent) or
  * 2N floats (coherent, interleaved re,im).                                                          */
 int gb200_correlation_profile(gb200_engine* e, int prn_idx, double doppler_hz, int n_ms, int integration_type,
