@@ -55,12 +55,15 @@ __global__ void __launch_bounds__(128) k_replica_spectra(const uint8_t* chips, f
 // ---------------------------------------------------------------------------------------------------------
 // doppler_spectra
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kSpecWarps = 8;
-constexpr int kSpecThreads = kSpecWarps * 32;
-constexpr int kCarrierTable = 64;  // ceil(16368 / 256)
+// One warp per (polyphase branch, bin parity) task, at most 8: a 2.046 Msps millisecond (4 tasks) gets a 128-thread
+// CTA so four CTAs share an SM.
+__host__ __device__ constexpr int spec_warps(int s) { return 2 * s >= 8 ? 8 : 2 * s; }
+constexpr int kCarrierTable = 64;  // >= ceil(N / threads) for every supported rate
 
 template <int S>
-__global__ void __launch_bounds__(kSpecThreads) k_doppler_spectra(const SpectraArgs a) {
+__global__ void __launch_bounds__(spec_warps(S) * 32) k_doppler_spectra(const SpectraArgs a) {
+    constexpr int kSpecWarps = spec_warps(S);
+    constexpr int kSpecThreads = kSpecWarps * 32;
     extern __shared__ __align__(16) float2 smem[];
     float2* ypoly = smem;                          // [S][1024], rows in zpos() order
     float2* tiles = smem + S * kFft;               // [kSpecWarps][kTileF2]
@@ -156,6 +159,7 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
     float2* tiles = tw2_s + kFft;          // [2*NP][kTileF2]
     PairPartial* partial = reinterpret_cast<PairPartial*>(tiles + 2 * NP * kTileF2);  // [2*NP]
     uint64_t* mbar = reinterpret_cast<uint64_t*>(partial + 2 * NP);
+    uint64_t* consumed = mbar + 1;  // [2*NP]: "the partner has finished reading this warp's exchange tile"
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pair = warp >> 1, h = warp & 1;
@@ -164,6 +168,7 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
 
     uint32_t parity = 0;
     if (threadIdx.x == 0) mbar_init(mbar, 1);
+    if (lane == 0) mbar_init(consumed + warp, 1);
     __syncthreads();
     if (threadIdx.x == 0) {
         mbar_expect_tx(mbar, 2 * kFft * sizeof(float2));
@@ -172,6 +177,11 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
     }
     mbar_wait(mbar, parity);
     parity ^= 1;
+    // Split-phase hand-back of the exchange tile: after reading the partner's tile a warp arrives on the partner's
+    // `consumed` barrier and carries on; the partner only waits for it right before it overwrites that tile (a whole
+    // load + spectrum product later), so the pair meets at ONE blocking barrier per transform instead of two.
+    uint32_t consumed_parity = 0;
+    bool tile_lent = false;  // true while the partner may still be reading this warp's tile
 
     const int cells_per_group = NP / a.rsplit;
     const int r_per_pair = a.s / a.rsplit;
@@ -270,6 +280,10 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
                         const float2* __restrict__ p = spec_u + (static_cast<size_t>(it * a.s + r) * 2 + h) * kFft;
                         load_mul_vec(re, im, lane, p, crep_h);
                     }
+                    if (tile_lent) {
+                        mbar_wait(consumed + warp, consumed_parity);
+                        consumed_parity ^= 1;
+                    }
                     // inverse warp FFT-1024 = forward transform on swapped re/im
                     wfft_phase1(im, re, lane, tw1_s, tile);
                     __syncwarp();
@@ -280,6 +294,9 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
                     float xr[16], xi[16];
                     if (h == 0) combine_even(re, im, lane, tw2_s, ptile, xr, xi);
                     else combine_odd(re, im, lane, tw2_s, ptile, xr, xi);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(consumed + (warp ^ 1));  // partner's tile is free again
+                    tile_lent = true;
                     if (KIND == kKindCoherent) {
 #pragma unroll
                         for (int jj = 0; jj < 16; ++jj) {
@@ -301,7 +318,6 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
 #pragma unroll
                         for (int jj = 0; jj < 16; ++jj) acc[jj] += gb_sqrt(xr[jj] * xr[jj] + xi[jj] * xi[jj]);
                     }
-                    pair_barrier(pair);  // partner has read my tile; the next phase 1 may overwrite it
                 }
                 Peak t;
                 float fsum;
@@ -476,10 +492,11 @@ cudaError_t launch_refine_finalize(int n_sv, const RefineState* st, const CellRe
 // launch wrappers
 // ---------------------------------------------------------------------------------------------------------
 size_t spectra_smem_bytes(int s) {
-    return (static_cast<size_t>(s) * kFft + kSpecWarps * kTileF2 + kCarrierTable) * sizeof(float2);
+    return (static_cast<size_t>(s) * kFft + spec_warps(s) * kTileF2 + kCarrierTable) * sizeof(float2);
 }
 size_t correlate_smem_bytes(int np) {
-    return (4 * static_cast<size_t>(kFft) + 2 * np * kTileF2) * sizeof(float2) + 2 * np * sizeof(PairPartial) + 16;
+    return (4 * static_cast<size_t>(kFft) + 2 * np * kTileF2) * sizeof(float2) + 2 * np * sizeof(PairPartial) + 16 +
+           2 * np * sizeof(uint64_t);
 }
 
 bool spectra_supports(int s) {
@@ -525,7 +542,7 @@ cudaError_t launch_doppler_spectra(const SpectraArgs& a, cudaStream_t st) {
     const int grid = a.n_units * a.M;
     const size_t sm = spectra_smem_bytes(a.s);
     switch (a.s) {
-#define GB_CASE(S) case S: k_doppler_spectra<S><<<grid, kSpecThreads, sm, st>>>(a); break;
+#define GB_CASE(S) case S: k_doppler_spectra<S><<<grid, spec_warps(S) * 32, sm, st>>>(a); break;
         GB_CASE(1) GB_CASE(2) GB_CASE(3) GB_CASE(4) GB_CASE(5) GB_CASE(6) GB_CASE(8) GB_CASE(10) GB_CASE(12) GB_CASE(16)
 #undef GB_CASE
         default: return cudaErrorInvalidValue;
