@@ -159,7 +159,6 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
     float2* tiles = tw2_s + kFft;          // [2*NP][kTileF2]
     PairPartial* partial = reinterpret_cast<PairPartial*>(tiles + 2 * NP * kTileF2);  // [2*NP]
     uint64_t* mbar = reinterpret_cast<uint64_t*>(partial + 2 * NP);
-    uint64_t* consumed = mbar + 1;  // [2*NP]: "the partner has finished reading this warp's exchange tile"
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pair = warp >> 1, h = warp & 1;
@@ -168,7 +167,6 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
 
     uint32_t parity = 0;
     if (threadIdx.x == 0) mbar_init(mbar, 1);
-    if (lane == 0) mbar_init(consumed + warp, 1);
     __syncthreads();
     if (threadIdx.x == 0) {
         mbar_expect_tx(mbar, 2 * kFft * sizeof(float2));
@@ -177,12 +175,6 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
     }
     mbar_wait(mbar, parity);
     parity ^= 1;
-    // Split-phase hand-back of the exchange tile: after reading the partner's tile a warp arrives on the partner's
-    // `consumed` barrier and carries on; the partner only waits for it right before it overwrites that tile (a whole
-    // load + spectrum product later), so the pair meets at ONE blocking barrier per transform instead of two.
-    uint32_t consumed_parity = 0;
-    bool tile_lent = false;  // true while the partner may still be reading this warp's tile
-
     const int cells_per_group = NP / a.rsplit;
     const int r_per_pair = a.s / a.rsplit;
     const int my_cell = pair / a.rsplit;  // cell slot inside the group
@@ -280,10 +272,6 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
                         const float2* __restrict__ p = spec_u + (static_cast<size_t>(it * a.s + r) * 2 + h) * kFft;
                         load_mul_vec(re, im, lane, p, crep_h);
                     }
-                    if (tile_lent) {
-                        mbar_wait(consumed + warp, consumed_parity);
-                        consumed_parity ^= 1;
-                    }
                     // inverse warp FFT-1024 = forward transform on swapped re/im
                     wfft_phase1(im, re, lane, tw1_s, tile);
                     __syncwarp();
@@ -294,9 +282,6 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
                     float xr[16], xi[16];
                     if (h == 0) combine_even(re, im, lane, tw2_s, ptile, xr, xi);
                     else combine_odd(re, im, lane, tw2_s, ptile, xr, xi);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(consumed + (warp ^ 1));  // partner's tile is free again
-                    tile_lent = true;
                     if (KIND == kKindCoherent) {
 #pragma unroll
                         for (int jj = 0; jj < 16; ++jj) {
@@ -318,6 +303,7 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
 #pragma unroll
                         for (int jj = 0; jj < 16; ++jj) acc[jj] += gb_sqrt(xr[jj] * xr[jj] + xi[jj] * xi[jj]);
                     }
+                    pair_barrier(pair);  // partner has read my tile; the next phase 1 may overwrite it
                 }
                 Peak t;
                 float fsum;
@@ -495,8 +481,7 @@ size_t spectra_smem_bytes(int s) {
     return (static_cast<size_t>(s) * kFft + spec_warps(s) * kTileF2 + kCarrierTable) * sizeof(float2);
 }
 size_t correlate_smem_bytes(int np) {
-    return (4 * static_cast<size_t>(kFft) + 2 * np * kTileF2) * sizeof(float2) + 2 * np * sizeof(PairPartial) + 16 +
-           2 * np * sizeof(uint64_t);
+    return (4 * static_cast<size_t>(kFft) + 2 * np * kTileF2) * sizeof(float2) + 2 * np * sizeof(PairPartial) + 16;
 }
 
 bool spectra_supports(int s) {
