@@ -100,7 +100,7 @@ struct gb200_engine {
     int64_t iq_samples = 0;
     int64_t launches = 0;
     size_t spec_budget_bytes = 80u << 20;
-    int np = 8, rsplit_override = 0;
+    int np_override = 0, rsplit_override = 0;
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[2];
     size_t ev_used[2] = {0, 0};
@@ -196,10 +196,17 @@ int gcd_int(int a, int b) { return b ? gcd_int(b, a % b) : a; }
 
 // How many warp pairs share one cell.  With plenty of cells per pair each pair keeps a whole cell (no cross-pair
 // merge, no CTA-wide barrier); small launches split a cell's polyphase branches over pairs to fill the machine.
-int pick_rsplit(const gb200_engine* e, long long n_cells) {
-    if (e->rsplit_override > 0 && e->s % e->rsplit_override == 0 && e->np % e->rsplit_override == 0) return e->rsplit_override;
-    if (n_cells >= 8LL * e->num_sms * e->np) return 1;
-    return gcd_int(e->s, e->np);
+int pick_rsplit(const gb200_engine* e, int np, long long n_cells) {
+    if (e->rsplit_override > 0 && e->s % e->rsplit_override == 0 && np % e->rsplit_override == 0) return e->rsplit_override;
+    if (n_cells >= 8LL * e->num_sms * np) return 1;
+    return gcd_int(e->s, np);
+}
+
+// Warp pairs per CTA: 10 (20 warps / SM) for single-millisecond non-coherent searches, 8 otherwise (the
+// multi-millisecond accumulators need the larger register budget).  GB200_NP=8 forces the 8-pair build.
+int pick_np(const gb200_engine* e, int M, int kind, bool profile) {
+    if (e->np_override == 8) return 8;
+    return (M == 1 && kind == GB200_NON_COHERENT && !profile) ? 10 : 8;
 }
 
 size_t unit_floats2(const gb200_engine* e, int M) { return static_cast<size_t>(M) * e->s * 2 * kFft; }
@@ -251,8 +258,9 @@ int run_grid(gb200_engine* e, int n_blocks, int M, const int32_t* prn_idx, int P
     nb = std::min(nb, n_blocks);
     GB_CUDA(e, e->spec.ensure(per_block * nb));
 
-    const int rsplit = pick_rsplit(e, static_cast<long long>(nb) * P * D);
-    const int cpg = e->np / rsplit;
+    const int np = pick_np(e, M, kind, false);
+    const int rsplit = pick_rsplit(e, np, static_cast<long long>(nb) * P * D);
+    const int cpg = np / rsplit;
     const int chunks = (D + cpg - 1) / cpg;
     for (int b0 = 0; b0 < n_blocks; b0 += nb) {
         const int nbb = std::min(nb, n_blocks - b0);
@@ -297,7 +305,7 @@ int run_grid(gb200_engine* e, int n_blocks, int M, const int32_t* prn_idx, int P
         const int grid = std::min(ca.n_groups, e->num_sms);
         {
             TimedLaunch tl(e, 1);
-            GB_CUDA(e, launch_correlate_cells(ca, e->np, grid, e->stream));
+            GB_CUDA(e, launch_correlate_cells(ca, np, grid, e->stream));
         }
         e->launches++;
     }
@@ -317,8 +325,9 @@ int run_cells(gb200_engine* e, int n_cells, const int32_t* prn_idx, const double
         if (prn_idx[i] < 0 || prn_idx[i] >= e->n_prn) GB_FAIL(e, GB200_EINVAL, "prn index %d out of range", prn_idx[i]);
     e->grid_cache_valid = false;  // d_ints / d_doppler are about to be overwritten
 
-    const int rsplit = pick_rsplit(e, n_cells);
-    const int cpg = e->np / rsplit;
+    const int np = pick_np(e, M, kind, profile_dev != nullptr);
+    const int rsplit = pick_rsplit(e, np, n_cells);
+    const int cpg = np / rsplit;
     std::vector<int> order(n_cells);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return prn_idx[a] < prn_idx[b]; });
@@ -422,7 +431,7 @@ int run_cells(gb200_engine* e, int n_cells, const int32_t* prn_idx, const double
         const int grid = std::min(ng, e->num_sms);
         {
             TimedLaunch tl(e, 1);
-            GB_CUDA(e, launch_correlate_cells(ca, e->np, grid, e->stream));
+            GB_CUDA(e, launch_correlate_cells(ca, np, grid, e->stream));
         }
         e->launches++;
         c0 = c1;
@@ -480,7 +489,7 @@ int gb200_create(int device, int fs, int n, gb200_engine** out) {
     e->N = n;
     e->s = n / kChips;
     e->spec_budget_bytes = static_cast<size_t>(env_int("GB200_SPEC_BUDGET_MB", 80)) << 20;
-    e->np = env_int("GB200_NP", 8) == 10 ? 10 : 8;
+    e->np_override = env_int("GB200_NP", 0);
     e->rsplit_override = env_int("GB200_RSPLIT", 0);
     auto fail = [&](cudaError_t c, const char* what) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(c);
@@ -670,8 +679,9 @@ int gb200_detect(gb200_engine* e, int n_sv, const int32_t* prn_idx, int n_ms, gb
 
     const int MAXB = kRefineMaxBins;
     const int n_cells = n_sv * MAXB;
-    const int rsplit = pick_rsplit(e, n_cells);
-    const int cpg = e->np / rsplit;
+    const int np = pick_np(e, n_ms, GB200_NON_COHERENT, false);
+    const int rsplit = pick_rsplit(e, np, n_cells);
+    const int cpg = np / rsplit;
     const int gps = (MAXB + cpg - 1) / cpg;  // groups per satellite
     const size_t unit = unit_floats2(e, n_ms);
     int sv_per_chunk = static_cast<int>(std::max<size_t>(1, e->spec_budget_bytes / (unit * sizeof(float2) * MAXB)));
@@ -776,7 +786,7 @@ int gb200_detect(gb200_engine* e, int n_sv, const int32_t* prn_idx, int n_ms, gb
             ca.cell_gate = e->r_doppler.p;
             {
                 TimedLaunch tl(e, 1);
-                GB_CUDA(e, launch_correlate_cells(ca, e->np, std::min(ca.n_groups, e->num_sms), e->stream));
+                GB_CUDA(e, launch_correlate_cells(ca, np, std::min(ca.n_groups, e->num_sms), e->stream));
             }
             e->launches++;
         }
@@ -792,6 +802,7 @@ int gb200_detect(gb200_engine* e, int n_sv, const int32_t* prn_idx, int n_ms, gb
         CorrelateArgs ca = base;
         ca.records = d_coh_records;
         ca.kind = GB200_COHERENT;
+        ca.rsplit = pick_rsplit(e, 8, n_sv);  // the coherent pass always runs on the 8-pair build
         ca.n_groups = n_sv;
         ca.cell_u = cbase;
         ca.cell_out = cbase + n_sv;
@@ -801,7 +812,7 @@ int gb200_detect(gb200_engine* e, int n_sv, const int32_t* prn_idx, int n_ms, gb
         ca.cell_probe = d_probe;
         ca.cell_gate = nullptr;
         TimedLaunch tl(e, 1);
-        GB_CUDA(e, launch_correlate_cells(ca, e->np, std::min(n_sv, e->num_sms), e->stream));
+        GB_CUDA(e, launch_correlate_cells(ca, 8, std::min(n_sv, e->num_sms), e->stream));
         e->launches++;
     }
     GB_CUDA(e, launch_refine_finalize(n_sv, e->r_state.p, d_coh_records, e->r_results.p, e->stream));

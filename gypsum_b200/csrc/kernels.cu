@@ -247,7 +247,9 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
                 float acc[16];
 #pragma unroll
                 for (int jj = 0; jj < 16; ++jj) acc[jj] = 0.f;
-                const int n_iter = (KIND == kKindCoherent) ? 1 : a.M;
+                // The 10-pair build (20 warps / SM, 96 registers) is only launched for single-millisecond non-coherent work:
+                // with the trip count known the accumulators are not live across the transform and nothing spills.
+                const int n_iter = (KIND == kKindCoherent || NP == 10) ? 1 : a.M;
                 for (int it = 0; it < n_iter; ++it) {
                     float re[32], im[32];
                     if (KIND == kKindCoherent) {
