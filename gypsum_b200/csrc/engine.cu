@@ -72,8 +72,7 @@ int env_int(const char* name, int dflt) {
 
 struct gb200_engine {
     int device = 0, fs = 0, N = 0, s = 0, num_sms = 148;
-    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t copy_event = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
     DevBuf<float2> tw1, tw2, crep, iq_own, spec;
     DevBuf<uint8_t> chips;
     DevBuf<double> d_doppler;
@@ -135,8 +134,6 @@ struct gb200_engine {
                 cudaEventDestroy(pr.first);
                 cudaEventDestroy(pr.second);
             }
-        if (copy_event) cudaEventDestroy(copy_event);
-        if (copy_stream) cudaStreamDestroy(copy_stream);
         if (own_stream) cudaStreamDestroy(own_stream);
     }
 };
@@ -224,15 +221,14 @@ int check_common(gb200_engine* e, int n_ms, int kind) {
 }
 
 // grid mode: all cells of n_blocks x prn list x doppler list; records written to rec_dev (device)
-// `first_block`: the grid starts at this block of the loaded IQ (used to pipeline one call in pieces).
 int run_grid(gb200_engine* e, int n_blocks, int M, const int32_t* prn_idx, int P, const double* dop, int D, int kind,
-             CellRecord* rec_dev, int first_block = 0) {
+             CellRecord* rec_dev) {
     int rc = check_common(e, M, kind);
     if (rc) return rc;
     if (n_blocks < 1 || P < 1 || D < 1 || !prn_idx || !dop) GB_FAIL(e, GB200_EINVAL, "empty grid");
-    if (static_cast<int64_t>(first_block + n_blocks) * M * e->N > e->iq_samples)
-        GB_FAIL(e, GB200_EINVAL, "grid needs %lld samples, %lld loaded",
-                static_cast<long long>(first_block + n_blocks) * M * e->N, static_cast<long long>(e->iq_samples));
+    if (static_cast<int64_t>(n_blocks) * M * e->N > e->iq_samples)
+        GB_FAIL(e, GB200_EINVAL, "grid needs %lld samples, %lld loaded", static_cast<long long>(n_blocks) * M * e->N,
+                static_cast<long long>(e->iq_samples));
     for (int i = 0; i < P; ++i)
         if (prn_idx[i] < 0 || prn_idx[i] >= e->n_prn) GB_FAIL(e, GB200_EINVAL, "prn index %d out of range", prn_idx[i]);
 
@@ -269,7 +265,7 @@ int run_grid(gb200_engine* e, int n_blocks, int M, const int32_t* prn_idx, int P
     for (int b0 = 0; b0 < n_blocks; b0 += nb) {
         const int nbb = std::min(nb, n_blocks - b0);
         SpectraArgs sa{};
-        sa.iq = e->iq + static_cast<size_t>(first_block + b0) * M * e->N;
+        sa.iq = e->iq + static_cast<size_t>(b0) * M * e->N;
         sa.doppler = e->d_doppler.p;
         sa.spec = e->spec.p;
         sa.tw1 = e->tw1.p;
@@ -605,28 +601,6 @@ int gb200_acquire_grid(gb200_engine* e, int n_blocks, int M, const int32_t* prn_
     if (n_blocks < 1 || P < 1 || D < 1) GB_FAIL(e, GB200_EINVAL, "empty grid");
     const size_t n = static_cast<size_t>(n_blocks) * P * D;
     GB_CUDA(e, e->d_records.ensure(n));
-    // Large batches going to a pinned caller buffer run as two halves so the device-to-host copy of the first half
-    // (on the copy stream) overlaps the kernels of the second.
-    if (n_blocks >= 8 && is_pinned_host(out_host)) {
-        if (!e->copy_stream) {
-            GB_CUDA(e, cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-            GB_CUDA(e, cudaEventCreateWithFlags(&e->copy_event, cudaEventDisableTiming));
-        }
-        const int nb0 = n_blocks / 2;
-        const size_t n0 = static_cast<size_t>(nb0) * P * D;
-        int rc = run_grid(e, nb0, M, prn_idx, P, dop, D, kind, e->d_records.p, 0);
-        if (rc) return rc;
-        GB_CUDA(e, cudaEventRecord(e->copy_event, e->stream));
-        GB_CUDA(e, cudaStreamWaitEvent(e->copy_stream, e->copy_event, 0));
-        GB_CUDA(e, cudaMemcpyAsync(out_host, e->d_records.p, n0 * sizeof(CellRecord), cudaMemcpyDeviceToHost, e->copy_stream));
-        rc = run_grid(e, n_blocks - nb0, M, prn_idx, P, dop, D, kind, e->d_records.p + n0, nb0);
-        if (rc) return rc;
-        GB_CUDA(e, cudaMemcpyAsync(out_host + n0, e->d_records.p + n0, (n - n0) * sizeof(CellRecord), cudaMemcpyDeviceToHost,
-                                   e->stream));
-        GB_CUDA(e, cudaStreamSynchronize(e->stream));
-        GB_CUDA(e, cudaStreamSynchronize(e->copy_stream));
-        return GB200_OK;
-    }
     int rc = run_grid(e, n_blocks, M, prn_idx, P, dop, D, kind, e->d_records.p);
     if (rc) return rc;
     return fetch_records(e, n, out_host);
