@@ -52,6 +52,7 @@ SYMBOLS = {
     "gb200_tracker_get_state": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                           C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "gb200_tracker_set_state": (C.c_int, [_P, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int32]),
+    "gb200_set_fused": (C.c_int, [_P, C.c_int]),
     "gb200_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "gb200_enable_kernel_timing": (C.c_int, [_P, C.c_int]),
     "gb200_kernel_timing": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
@@ -128,6 +129,10 @@ class Engine:
         n = C.c_int64()
         self._check(self._lib.gb200_launch_count(self._h, C.byref(n)), "gb200_launch_count")
         return n.value
+
+    def set_fused(self, on: bool) -> None:
+        """Select the single fused block-per-(PRN, Doppler) kernel for acquire_cells (comparison / north-star shape)."""
+        self._check(self._lib.gb200_set_fused(self._h, int(bool(on))), "gb200_set_fused")
 
     def enable_kernel_timing(self, on: bool) -> None:
         self._check(self._lib.gb200_enable_kernel_timing(self._h, int(bool(on))), "gb200_enable_kernel_timing")

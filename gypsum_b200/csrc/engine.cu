@@ -102,6 +102,8 @@ struct gb200_engine {
     size_t spec_budget_bytes = 80u << 20;
     int np_override = 0, rsplit_override = 0;
     bool timing = false;
+    bool fused = false;
+    bool fused_configured = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[2];
     size_t ev_used[2] = {0, 0};
     std::string err;
@@ -324,6 +326,41 @@ int run_cells(gb200_engine* e, int n_cells, const int32_t* prn_idx, const double
     for (int i = 0; i < n_cells; ++i)
         if (prn_idx[i] < 0 || prn_idx[i] >= e->n_prn) GB_FAIL(e, GB200_EINVAL, "prn index %d out of range", prn_idx[i]);
     e->grid_cache_valid = false;  // d_ints / d_doppler are about to be overwritten
+
+    if (e->fused && fused_supports(e->s) && !profile_dev) {
+        // one CTA per cell, whole pipeline in one kernel
+        GB_CUDA(e, cudaStreamSynchronize(e->stream));
+        GB_CUDA(e, e->d_ints.ensure(static_cast<size_t>(n_cells) * 2));
+        GB_CUDA(e, e->h_ints.ensure(static_cast<size_t>(n_cells) * 2));
+        GB_CUDA(e, e->d_doppler.ensure(n_cells));
+        GB_CUDA(e, e->h_doubles.ensure(n_cells));
+        for (int i = 0; i < n_cells; ++i) {
+            e->h_ints.p[i] = prn_idx[i];
+            e->h_ints.p[n_cells + i] = probe ? probe[i] : -1;
+            e->h_doubles.p[i] = dop[i];
+        }
+        GB_CUDA(e, cudaMemcpyAsync(e->d_ints.p, e->h_ints.p, sizeof(int) * 2 * n_cells, cudaMemcpyHostToDevice, e->stream));
+        GB_CUDA(e, cudaMemcpyAsync(e->d_doppler.p, e->h_doubles.p, sizeof(double) * n_cells, cudaMemcpyHostToDevice, e->stream));
+        FusedArgs fa{};
+        fa.iq = e->iq;
+        fa.doppler = e->d_doppler.p;
+        fa.prn = e->d_ints.p;
+        fa.probe = e->d_ints.p + n_cells;
+        fa.records = rec_dev;
+        fa.crep = e->crep.p;
+        fa.tw1 = e->tw1.p;
+        fa.tw2 = e->tw2.p;
+        fa.inv_fs = 1.0 / static_cast<double>(e->fs);
+        fa.N = e->N;
+        fa.M = M;
+        fa.n_cells = n_cells;
+        {
+            TimedLaunch tl(e, 1);
+            GB_CUDA(e, launch_acquire_fused(fa, e->s, kind, e->stream));
+        }
+        e->launches++;
+        return GB200_OK;
+    }
 
     const int np = pick_np(e, M, kind, profile_dev != nullptr);
     const int rsplit = pick_rsplit(e, np, n_cells);
@@ -970,6 +1007,18 @@ int gb200_tracker_set_state(gb200_tracker* t, int channel, double doppler_hz, do
     st.phase_acc = phase_acc;
     st.code_phase = code_phase;
     GB_CUDA(e, cudaMemcpy(t->states.p + channel, &st, head, cudaMemcpyHostToDevice));
+    return GB200_OK;
+}
+
+int gb200_set_fused(gb200_engine* e, int on) {
+    if (!e) return GB200_EINVAL;
+    if (on && !fused_supports(e->s)) GB_FAIL(e, GB200_EINVAL, "the fused kernel needs 2046 or 4092 samples per ms");
+    GB_CUDA(e, cudaSetDevice(e->device));
+    if (on && !e->fused_configured) {
+        GB_CUDA(e, configure_fused_kernel());
+        e->fused_configured = true;
+    }
+    e->fused = on != 0;
     return GB200_OK;
 }
 

@@ -80,6 +80,23 @@ struct TrackArgs {
     int N, s, n_ms, n_channels;
 };
 
+// acquire_fused: one CTA per (PRN, Doppler) cell, the whole pipeline in one kernel (fused.cu).
+struct FusedArgs {
+    const float2* iq;       // [M*N] one block
+    const double* doppler;  // [n_cells]
+    const int* prn;         // [n_cells] replica row
+    const int* probe;       // [n_cells] coherent probe index or -1 (may be null)
+    CellRecord* records;    // [n_cells]
+    const float2* crep;
+    const float2* tw1;
+    const float2* tw2;
+    double inv_fs;
+    int N, M, n_cells;
+};
+bool fused_supports(int s);
+cudaError_t configure_fused_kernel();
+cudaError_t launch_acquire_fused(const FusedArgs& a, int s, int kind, cudaStream_t st);
+
 size_t track_smem_bytes(int N, int s);
 cudaError_t configure_track_kernel();
 cudaError_t launch_track_channels(const TrackArgs& a, cudaStream_t st);

@@ -147,6 +147,12 @@ int gb200_tracker_get_state(gb200_tracker* t, int channel, double* doppler_hz, d
 int gb200_tracker_set_state(gb200_tracker* t, int channel, double doppler_hz, double carrier_phase, double phase_acc,
                             int32_t code_phase);
 
+/* Kernel selection for gb200_acquire_cells / gb200_acquire_grid: 0 (default) = doppler_spectra + correlate_cells
+ * (the PRN-independent half of the pipeline computed once per Doppler bin); 1 = the single fused
+ * block-per-(PRN, Doppler) kernel (every cell redoes wipe-off and forward transform; 2046 / 4092 samples per ms
+ * only).  Results agree to float32 rounding; the fused kernel exists for comparison.        */
+int gb200_set_fused(gb200_engine* e, int on);
+
 /* Kernels launched by this engine so far (bench.py's gpu_launches). */
 int gb200_launch_count(const gb200_engine* e, int64_t* out);
 

@@ -78,6 +78,30 @@ def grid_case(name, n, m, n_dop, n_blocks, reps):
     eng.close()
 
 
+def fused_case(n, m, n_dop, reps):
+    """Same cells through the fused block-per-(PRN, Doppler) kernel and through the de-duplicated pair (list mode)."""
+    fs = n * 1000
+    eng = _native.Engine(fs, n)
+    eng.set_replicas(CHIPS)
+    x = noise(n * m, 1)
+    eng.upload_iq(x)
+    dop = np.linspace(-10000, 10000, n_dop)
+    prn = np.repeat(np.arange(32), n_dop)
+    dd = np.tile(dop, 32)
+    out = {}
+    for name, on in (("split", False), ("fused", True)):
+        eng.set_fused(on)
+        eng.acquire_cells(prn, dd, m)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            eng.acquire_cells(prn, dd, m)
+        out[name] = (time.perf_counter() - t0) / reps * 1e3
+    eng.set_fused(False)
+    print(json.dumps({"workload": f"fused vs split kernels, list of 32x{n_dop} cells, {m} ms @ N={n} (host to host)",
+                      "split_ms": out["split"], "fused_ms": out["fused"]}), flush=True)
+    eng.close()
+
+
 def detector_case():
     from gypsum_b200.acquisition import GpsSatelliteDetector
     from gypsum_b200.gps_ca_prn_codes import GpsSatelliteId, generate_replica_prn_signals
@@ -134,5 +158,7 @@ if __name__ == "__main__":
     grid_case("config 2 x 32 blocks", 2046, 1, 41, 32, 50)
     grid_case("config 3: 32x41x10 ms @ 4.092 Msps", 4092, 10, 41, 1, 20)
     grid_case("config 5 shape: 32x81 @ 16.368 Msps, 1-ms blocks", 16368, 1, 81, 4 if quick else 16, 5)
+    fused_case(2046, 1, 41, 50)
+    fused_case(2046, 10, 24, 10)
     detector_case()
     tracker_case(32, 5000 if quick else 60000)
