@@ -85,6 +85,8 @@ struct gb200_engine {
     DevBuf<CellRecord> r_records;
     DevBuf<int> r_ints;
     DevBuf<RefineResult> r_results;
+    DevBuf<int> r_cell_prn;
+    PinnedBuf<int> rh_cell_prn;
     PinnedBuf<int> rh_ints;
     PinnedBuf<RefineResult> rh_results;
     PinnedBuf<float2> h_iq;
@@ -103,6 +105,7 @@ struct gb200_engine {
     int np_override = 0, rsplit_override = 0;
     bool timing = false;
     bool fused = false;
+    bool detect_fused = true;  // gb200_detect: fused block-per-cell kernel (every cell has its own Doppler)
     bool fused_configured = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[2];
     size_t ev_used[2] = {0, 0};
@@ -124,6 +127,8 @@ struct gb200_engine {
         r_records.release();
         r_ints.release();
         r_results.release();
+        r_cell_prn.release();
+        rh_cell_prn.release();
         rh_ints.release();
         rh_results.release();
         h_iq.release();
@@ -528,6 +533,7 @@ int gb200_create(int device, int fs, int n, gb200_engine** out) {
     e->spec_budget_bytes = static_cast<size_t>(env_int("GB200_SPEC_BUDGET_MB", 80)) << 20;
     e->np_override = env_int("GB200_NP", 0);
     e->rsplit_override = env_int("GB200_RSPLIT", 0);
+    e->detect_fused = env_int("GB200_DETECT_FUSED", 1) != 0;
     auto fail = [&](cudaError_t c, const char* what) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(c);
         cudaGetLastError();
@@ -802,12 +808,53 @@ int gb200_detect(gb200_engine* e, int n_sv, const int32_t* prn_idx, int n_ms, gb
     base.rsplit = rsplit;
     base.grid_mode = 0;
 
+    // Every (satellite, bin) cell of a refinement pass has its own Doppler, so nothing is shared between PRNs: the
+    // fused block-per-cell kernel does the same arithmetic without the spectra round trip through HBM.
+    const bool use_fused = fused_supports(e->s) && e->detect_fused;
+    FusedArgs fbase{};
+    const int* d_cell_prn = nullptr;
+    if (use_fused) {
+        if (!e->fused_configured) {
+            GB_CUDA(e, configure_fused_kernel());
+            e->fused_configured = true;
+        }
+        // [n_cells] replica row of every (satellite, bin) slot, then [n_sv] one per satellite for the coherent pass
+        GB_CUDA(e, e->r_cell_prn.ensure(static_cast<size_t>(n_cells) + n_sv));
+        GB_CUDA(e, e->rh_cell_prn.ensure(static_cast<size_t>(n_cells) + n_sv));
+        for (int c = 0; c < n_cells; ++c) e->rh_cell_prn.p[c] = prn_idx[c / MAXB];
+        for (int sv = 0; sv < n_sv; ++sv) e->rh_cell_prn.p[n_cells + sv] = prn_idx[sv];
+        GB_CUDA(e, cudaMemcpyAsync(e->r_cell_prn.p, e->rh_cell_prn.p, sizeof(int) * (n_cells + n_sv), cudaMemcpyHostToDevice,
+                                   e->stream));
+        d_cell_prn = e->r_cell_prn.p;
+        fbase.iq = e->iq;
+        fbase.crep = e->crep.p;
+        fbase.tw1 = e->tw1.p;
+        fbase.tw2 = e->tw2.p;
+        fbase.inv_fs = 1.0 / static_cast<double>(e->fs);
+        fbase.N = e->N;
+        fbase.M = n_ms;
+    }
+
     GB_CUDA(e, launch_refine_init(n_sv, e->r_state.p, e->stream));
     e->launches++;
     for (double spread = 7000.0; spread >= 10.0; spread /= 2.0) {  // acquisition.py:78-89
         GB_CUDA(e, launch_refine_plan(n_sv, spread, e->r_state.p, e->r_doppler.p, e->stream));
         e->launches++;
-        for (int sv0 = 0; sv0 < n_sv; sv0 += sv_per_chunk) {
+        if (use_fused) {
+            // one launch per pass: a CTA per (satellite, bin) slot, no spectra scratch
+            FusedArgs fa = fbase;
+            fa.doppler = e->r_doppler.p;
+            fa.prn = d_cell_prn;
+            fa.probe = nullptr;
+            fa.records = e->r_records.p;
+            fa.n_cells = n_cells;
+            {
+                TimedLaunch tl(e, 1);
+                GB_CUDA(e, launch_acquire_fused(fa, e->s, GB200_NON_COHERENT, e->stream));
+            }
+            e->launches++;
+        }
+        for (int sv0 = 0; !use_fused && sv0 < n_sv; sv0 += sv_per_chunk) {
             const int nsv = std::min(sv_per_chunk, n_sv - sv0);
             GB_CUDA(e, spectra(e->r_doppler.p + static_cast<size_t>(sv0) * MAXB, nsv * MAXB));
             CorrelateArgs ca = base;
@@ -833,8 +880,22 @@ int gb200_detect(gb200_engine* e, int n_sv, const int32_t* prn_idx, int n_ms, gb
     // coherent integration at the kept Doppler (acquisition.py:120-136)
     GB_CUDA(e, launch_refine_coherent_plan(n_sv, e->r_state.p, d_coh_doppler, d_probe, e->stream));
     e->launches++;
-    GB_CUDA(e, spectra(d_coh_doppler, n_sv));
-    {
+    if (use_fused) {
+        FusedArgs fa = fbase;
+        fa.doppler = d_coh_doppler;
+        fa.prn = d_cell_prn + n_cells;
+        fa.probe = d_probe;
+        fa.records = d_coh_records;
+        fa.n_cells = n_sv;
+        {
+            TimedLaunch tl(e, 1);
+            GB_CUDA(e, launch_acquire_fused(fa, e->s, GB200_COHERENT, e->stream));
+        }
+        e->launches++;
+    } else {
+        GB_CUDA(e, spectra(d_coh_doppler, n_sv));
+    }
+    if (!use_fused) {
         const int* cbase = di + 2 * n_cells + 3 * ng;
         CorrelateArgs ca = base;
         ca.records = d_coh_records;

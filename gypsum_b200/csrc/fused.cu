@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(2 * S * 32, 1) k_acquire_fused(const FusedArgs
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int r = warp >> 1, h = warp & 1;
     const double f = a.doppler[cell];
+    if (isnan(f)) return;  // slot switched off by the on-device search planner (uniform for the whole CTA)
     const int prn = a.prn[cell];
     const int probe = (KIND == kKindCoherent && a.probe) ? a.probe[cell] : -1;
     const uint32_t chunk_bytes = static_cast<uint32_t>(a.N) * sizeof(float2);

@@ -89,16 +89,23 @@ def fused_case(n, m, n_dop, reps):
     prn = np.repeat(np.arange(32), n_dop)
     dd = np.tile(dop, 32)
     out = {}
-    for name, on in (("split", False), ("fused", True)):
-        eng.set_fused(on)
-        eng.acquire_cells(prn, dd, m)
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            eng.acquire_cells(prn, dd, m)
-        out[name] = (time.perf_counter() - t0) / reps * 1e3
+    for label, dops in (("shared Doppler bins", dd), ("unique Doppler per cell", dd + np.arange(dd.size) * 0.37)):
+        for name, on in (("split", False), ("fused", True)):
+            eng.set_fused(on)
+            eng.acquire_cells(prn, dops, m)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                eng.acquire_cells(prn, dops, m)
+            host_ms = (time.perf_counter() - t0) / reps * 1e3
+            eng.enable_kernel_timing(True)
+            for _ in range(reps):
+                eng.acquire_cells(prn, dops, m)
+            k0, _n0 = eng.kernel_timing(0)
+            k1, _n1 = eng.kernel_timing(1)
+            eng.enable_kernel_timing(False)
+            out[f"{label}: {name}"] = {"host_to_host_ms": host_ms, "kernels_ms": (k0 + k1) / reps}
     eng.set_fused(False)
-    print(json.dumps({"workload": f"fused vs split kernels, list of 32x{n_dop} cells, {m} ms @ N={n} (host to host)",
-                      "split_ms": out["split"], "fused_ms": out["fused"]}), flush=True)
+    print(json.dumps({"workload": f"fused vs split kernels, list of 32x{n_dop} cells, {m} ms @ N={n}", **out}), flush=True)
     eng.close()
 
 
@@ -122,6 +129,7 @@ def detector_case():
         found = det.detect_satellites_in_antenna_data(ids, x, A)
         ts.append(time.perf_counter() - t0)
     print(json.dumps({"workload": "real detector: 32 SV x 10 passes (222 bins) + coherent, 10 ms @ 2.046 Msps",
+                      "detect_kernel": os.environ.get("GB200_DETECT_FUSED", "1") != "0" and "fused" or "split",
                       "seconds_per_scan": float(np.median(ts)), "cell_ms_per_scan": 32 * 223 * 10,
                       "found": [[r.satellite_id.id, r.doppler_shift, r.prn_phase_shift] for r in found]}), flush=True)
 
