@@ -130,9 +130,11 @@ class Engine:
         self._check(self._lib.gb200_launch_count(self._h, C.byref(n)), "gb200_launch_count")
         return n.value
 
-    def set_fused(self, on: bool) -> None:
-        """Select the single fused block-per-(PRN, Doppler) kernel for acquire_cells (comparison / north-star shape)."""
-        self._check(self._lib.gb200_set_fused(self._h, int(bool(on))), "gb200_set_fused")
+    def set_fused(self, mode) -> None:
+        """acquire_cells kernel choice: True / 1 = fused block-per-(PRN, Doppler) kernel, False / 0 = doppler_spectra +
+        correlate_cells, None / -1 = automatic (default)."""
+        m = -1 if mode is None else int(mode)
+        self._check(self._lib.gb200_set_fused(self._h, m), "gb200_set_fused")
 
     def enable_kernel_timing(self, on: bool) -> None:
         self._check(self._lib.gb200_enable_kernel_timing(self._h, int(bool(on))), "gb200_enable_kernel_timing")

@@ -104,7 +104,7 @@ struct gb200_engine {
     size_t spec_budget_bytes = 80u << 20;
     int np_override = 0, rsplit_override = 0;
     bool timing = false;
-    bool fused = false;
+    int fused = -1;  // acquire_cells kernel choice: -1 automatic, 0 doppler_spectra + correlate_cells, 1 fused block-per-cell
     bool detect_fused = true;  // gb200_detect: fused block-per-cell kernel (every cell has its own Doppler)
     bool fused_configured = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[2];
@@ -332,7 +332,21 @@ int run_cells(gb200_engine* e, int n_cells, const int32_t* prn_idx, const double
         if (prn_idx[i] < 0 || prn_idx[i] >= e->n_prn) GB_FAIL(e, GB200_EINVAL, "prn index %d out of range", prn_idx[i]);
     e->grid_cache_valid = false;  // d_ints / d_doppler are about to be overwritten
 
-    if (e->fused && fused_supports(e->s) && !profile_dev) {
+    bool use_fused = e->fused == 1;
+    if (e->fused < 0 && fused_supports(e->s) && !profile_dev) {
+        // Automatic choice.  The split kernels pay off when many cells share a Doppler bin (the PRN-independent half is
+        // computed once per bin); lists with mostly distinct Dopplers (the refinement passes of acquisition.py:81-101)
+        // and small lists are faster through the fused block-per-cell kernel (profiles/configs_r1l.jsonl).
+        std::vector<double> u(dop, dop + n_cells);
+        std::sort(u.begin(), u.end());
+        const long long n_unique = std::unique(u.begin(), u.end()) - u.begin();
+        use_fused = n_unique * 4 > n_cells || static_cast<long long>(n_cells) * M <= 8192;
+    }
+    if (use_fused && fused_supports(e->s) && !profile_dev) {
+        if (!e->fused_configured) {
+            GB_CUDA(e, configure_fused_kernel());
+            e->fused_configured = true;
+        }
         // one CTA per cell, whole pipeline in one kernel
         GB_CUDA(e, cudaStreamSynchronize(e->stream));
         GB_CUDA(e, e->d_ints.ensure(static_cast<size_t>(n_cells) * 2));
@@ -1071,15 +1085,11 @@ int gb200_tracker_set_state(gb200_tracker* t, int channel, double doppler_hz, do
     return GB200_OK;
 }
 
-int gb200_set_fused(gb200_engine* e, int on) {
+int gb200_set_fused(gb200_engine* e, int mode) {
     if (!e) return GB200_EINVAL;
-    if (on && !fused_supports(e->s)) GB_FAIL(e, GB200_EINVAL, "the fused kernel needs 2046 or 4092 samples per ms");
-    GB_CUDA(e, cudaSetDevice(e->device));
-    if (on && !e->fused_configured) {
-        GB_CUDA(e, configure_fused_kernel());
-        e->fused_configured = true;
-    }
-    e->fused = on != 0;
+    if (mode < -1 || mode > 1) GB_FAIL(e, GB200_EINVAL, "mode must be -1 (automatic), 0 or 1");
+    if (mode == 1 && !fused_supports(e->s)) GB_FAIL(e, GB200_EINVAL, "the fused kernel needs 2046 or 4092 samples per ms");
+    e->fused = mode;
     return GB200_OK;
 }
 

@@ -22,17 +22,20 @@ struct FusedPartial {
     int pad;
 };
 
+// Shared memory per CTA (2.046 Msps): IQ chunk 16 KB + replica spectrum 16 KB + 4 transpose tiles 34 KB = 67 KB, so
+// three CTAs (12 transform warps) share an SM.  The polyphase rows live inside the tile area (they are dead once the
+// transforms start) and the twiddle tables are read through L1 from global memory (every CTA reads the same 16 KB).
 template <int S, int KIND>
-__global__ void __launch_bounds__(2 * S * 32, 1) k_acquire_fused(const FusedArgs a) {
+__global__ void __launch_bounds__(2 * S * 32, (S == 2 ? 3 : 1)) k_acquire_fused(const FusedArgs a) {
     constexpr int kWarps = 2 * S;
     constexpr int kThreads = kWarps * 32;
     extern __shared__ __align__(16) float2 smem[];
     float2* iqbuf = smem;                  // [N]      one millisecond of IQ (TMA destination)
-    float2* ypoly = iqbuf + a.N;           // [S][1024]
-    float2* crep_s = ypoly + S * kFft;     // [2][1024]
-    float2* tw1_s = crep_s + 2 * kFft;
-    float2* tw2_s = tw1_s + kFft;
-    float2* tiles = tw2_s + kFft;          // [2S][kTileF2]
+    float2* crep_s = iqbuf + a.N;          // [2][1024]
+    float2* tiles = crep_s + 2 * kFft;     // [2S][kTileF2]
+    float2* ypoly = tiles;                 // [S][1024] aliases the tiles: written by the wipe-off, read by build_z only
+    const float2* __restrict__ tw1_s = a.tw1;
+    const float2* __restrict__ tw2_s = a.tw2;
     FusedPartial* partial = reinterpret_cast<FusedPartial*>(tiles + kWarps * kTileF2);  // [2S]
     float2* coarse = reinterpret_cast<float2*>(partial + kWarps);                      // [32]
     uint64_t* mbar = reinterpret_cast<uint64_t*>(coarse + 32);                          // [2]: tables, IQ chunk
@@ -52,9 +55,7 @@ __global__ void __launch_bounds__(2 * S * 32, 1) k_acquire_fused(const FusedArgs
     }
     __syncthreads();
     if (tid == 0) {
-        mbar_expect_tx(mbar, 4 * kFft * sizeof(float2));
-        bulk_g2s(tw1_s, a.tw1, kFft * sizeof(float2), mbar);
-        bulk_g2s(tw2_s, a.tw2, kFft * sizeof(float2), mbar);
+        mbar_expect_tx(mbar, 2 * kFft * sizeof(float2));
         bulk_g2s(crep_s, a.crep + static_cast<size_t>(prn) * 2 * kFft, 2 * kFft * sizeof(float2), mbar);
         mbar_expect_tx(mbar + 1, chunk_bytes);
         bulk_g2s(iqbuf, a.iq, chunk_bytes, mbar + 1);  // millisecond 0
@@ -194,8 +195,7 @@ __global__ void __launch_bounds__(2 * S * 32, 1) k_acquire_fused(const FusedArgs
 }
 
 size_t fused_smem_bytes(int N, int s) {
-    return (static_cast<size_t>(N) + static_cast<size_t>(s) * kFft + 4 * kFft + 2 * static_cast<size_t>(s) * kTileF2 + 32) *
-               sizeof(float2) +
+    return (static_cast<size_t>(N) + 2 * kFft + 2 * static_cast<size_t>(s) * kTileF2 + 32) * sizeof(float2) +
            2 * s * sizeof(FusedPartial) + 32;
 }
 

@@ -147,11 +147,16 @@ int gb200_tracker_get_state(gb200_tracker* t, int channel, double* doppler_hz, d
 int gb200_tracker_set_state(gb200_tracker* t, int channel, double doppler_hz, double carrier_phase, double phase_acc,
                             int32_t code_phase);
 
-/* Kernel selection for gb200_acquire_cells / gb200_acquire_grid: 0 (default) = doppler_spectra + correlate_cells
- * (the PRN-independent half of the pipeline computed once per Doppler bin); 1 = the single fused
- * block-per-(PRN, Doppler) kernel (every cell redoes wipe-off and forward transform; 2046 / 4092 samples per ms
- * only).  Results agree to float32 rounding; the fused kernel exists for comparison.        */
-int gb200_set_fused(gb200_engine* e, int on);
+/* Kernel selection for gb200_acquire_cells.  Two implementations of the same arithmetic exist:
+ *   0  doppler_spectra + correlate_cells: the PRN-independent half of the pipeline (wipe-off, forward transform) is
+ *      computed once per distinct Doppler bin and shared by every PRN -- the grid shape (gb200_acquire_grid always
+ *      uses it);
+ *   1  the single fused block-per-(PRN, Doppler) kernel: IQ chunk and replica spectrum staged by TMA, whole
+ *      pipeline in one CTA (2046 / 4092 samples per ms only) -- best when every cell has its own Doppler, as in
+ *      the refinement passes of acquisition.py:81-101 (gb200_detect uses it);
+ *  -1  (default) choose per call from the number of distinct Doppler values.
+ * Results agree to float32 rounding.                                                                   */
+int gb200_set_fused(gb200_engine* e, int mode);
 
 /* Kernels launched by this engine so far (bench.py's gpu_launches). */
 int gb200_launch_count(const gb200_engine* e, int64_t* out);

@@ -104,7 +104,7 @@ def fused_case(n, m, n_dop, reps):
             k1, _n1 = eng.kernel_timing(1)
             eng.enable_kernel_timing(False)
             out[f"{label}: {name}"] = {"host_to_host_ms": host_ms, "kernels_ms": (k0 + k1) / reps}
-    eng.set_fused(False)
+    eng.set_fused(None)
     print(json.dumps({"workload": f"fused vs split kernels, list of 32x{n_dop} cells, {m} ms @ N={n}", **out}), flush=True)
     eng.close()
 
