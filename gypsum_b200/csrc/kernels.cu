@@ -161,14 +161,9 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
     uint64_t* mbar = reinterpret_cast<uint64_t*>(partial + 2 * NP);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // The two warps of a pair sit on the SAME scheduler (warp ids w and w+4 share an SM sub-partition): they compete
-    // for the same issue port, advance in near lock-step, and meet at the pair barriers with little skew.  (With 20
-    // warps the last four -- one per sub-partition -- pair up across neighbours.)
-    const int pair = warp < 16 ? (warp & 3) + 4 * (warp >> 3) : 8 + ((warp - 16) >> 1);
-    const int h = warp < 16 ? (warp >> 2) & 1 : warp & 1;
-    const int partner = warp < 16 ? warp ^ 4 : warp ^ 1;
+    const int pair = warp >> 1, h = warp & 1;
     float2* tile = tiles + warp * kTileF2;
-    const float2* ptile = tiles + partner * kTileF2;
+    const float2* ptile = tiles + (warp ^ 1) * kTileF2;
 
     uint32_t parity = 0;
     if (threadIdx.x == 0) mbar_init(mbar, 1);
@@ -342,7 +337,7 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
                 pp.pr_re = pr_re;
                 pp.pr_im = pr_im;
                 pp.pad = 0;
-                partial[2 * pair + h] = pp;
+                partial[warp] = pp;
             }
         }
         // ---- merge the 2*rsplit warp partials of each cell and write its record ----
@@ -356,7 +351,7 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
             peak_init(m);
             float pre = 0.f, pim = 0.f;
             for (int w = 0; w < 2 * a.rsplit; ++w) {
-                const PairPartial pp = partial[2 * pair + w];
+                const PairPartial pp = partial[warp + w];
                 Peak o;
                 o.mx = pp.mx;
                 o.idx = pp.idx;
