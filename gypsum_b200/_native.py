@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgypsum_b200.so")
+LIB_PATH = os.environ.get("GB200_LIB") or os.path.join(_HERE, "libgypsum_b200.so")  # GB200_LIB: experiment builds
 
 OK, EINVAL, ECUDA, ESTATE = 0, 1, 2, 3
 COHERENT, NON_COHERENT = 1, 2
