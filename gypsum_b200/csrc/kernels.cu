@@ -159,7 +159,6 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
     float2* tiles = tw2_s + kFft;          // [2*NP][kTileF2]
     PairPartial* partial = reinterpret_cast<PairPartial*>(tiles + 2 * NP * kTileF2);  // [2*NP]
     uint64_t* mbar = reinterpret_cast<uint64_t*>(partial + 2 * NP);
-    uint64_t* pf_bar = mbar + 1;  // [2*NP] one per warp: "the next half-spectrum has landed in this warp's tile"
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pair = warp >> 1, h = warp & 1;
@@ -168,13 +167,7 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
 
     uint32_t parity = 0;
     if (threadIdx.x == 0) mbar_init(mbar, 1);
-    if (lane == 0) mbar_init(pf_bar + warp, 1);
     __syncthreads();
-    // Asynchronous prefetch (non-coherent path): as soon as the partner has finished with this warp's tile, one lane
-    // issues a TMA bulk copy of the NEXT transform's 8 KB half-spectrum into it; the copy lands behind the reduction
-    // of the current transform, so the next transform starts from shared memory instead of waiting on L2.
-    uint32_t pf_parity = 0;
-    bool pf_valid = false;
     if (threadIdx.x == 0) {
         mbar_expect_tx(mbar, 2 * kFft * sizeof(float2));
         bulk_g2s(tw1_s, a.tw1, kFft * sizeof(float2), mbar);
@@ -229,17 +222,6 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
         }
         bool active = my_cell < n_cells;
         if (active && a.cell_gate) active = !isnan(a.cell_gate[out]);
-        // the same cell slot in the next group of this CTA's range (prefetch target after this cell's last transform)
-        int next_unit = -1;
-        if (KIND != kKindCoherent && g + 1 < g1) {
-            if (a.grid_mode) {  // gb / gpl / gch already describe group g + 1
-                const int d = gch * cells_per_group + my_cell;
-                if (d < a.D) next_unit = gb * a.D + d;
-            } else if (my_cell < a.grp_count[g + 1]) {
-                const int c = a.grp_first[g + 1] + my_cell;
-                if (!a.cell_gate || !isnan(a.cell_gate[a.cell_out[c]])) next_unit = a.cell_u[c];
-            }
-        }
 
         // ---- stage conj(FFT(replica)) of this PRN: TMA bulk copy into shared memory ----
         if (prn != cur_prn) {
@@ -251,7 +233,6 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
             mbar_wait(mbar, parity);
             parity ^= 1;
             cur_prn = prn;
-            __nanosleep(pair * 300);  // de-phase the pairs after the CTA-wide barrier (measured: -4 % on config 2)
         }
 
         if (active) {
@@ -290,15 +271,8 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
                         }
                         mul_vec(re, im, lane, crep_h);
                     } else {
-                        if (pf_valid) {
-                            mbar_wait(pf_bar + warp, pf_parity);
-                            pf_parity ^= 1;
-                            load_mul_vec(re, im, lane, tile, crep_h);
-                            __syncwarp();  // every lane has read its elements before phase 1 overwrites the tile
-                        } else {
-                            const float2* __restrict__ p = spec_u + (static_cast<size_t>(it * a.s + r) * 2 + h) * kFft;
-                            load_mul_vec(re, im, lane, p, crep_h);
-                        }
+                        const float2* __restrict__ p = spec_u + (static_cast<size_t>(it * a.s + r) * 2 + h) * kFft;
+                        load_mul_vec(re, im, lane, p, crep_h);
                     }
                     // inverse warp FFT-1024 = forward transform on swapped re/im
                     wfft_phase1(im, re, lane, tw1_s, tile);
@@ -332,19 +306,6 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
                         for (int jj = 0; jj < 16; ++jj) acc[jj] += gb_sqrt(xr[jj] * xr[jj] + xi[jj] * xi[jj]);
                     }
                     pair_barrier(pair);  // partner has read my tile; the next phase 1 may overwrite it
-                    if (KIND != kKindCoherent) {
-                        const float2* nxt = nullptr;
-                        if (it + 1 < n_iter) nxt = spec_u + (static_cast<size_t>((it + 1) * a.s + r) * 2 + h) * kFft;
-                        else if (r + 1 < my_r0 + r_per_pair) nxt = spec_u + (static_cast<size_t>(r + 1) * 2 + h) * kFft;
-                        else if (next_unit >= 0)
-                            nxt = a.spec + static_cast<size_t>(next_unit) * unit_stride + (static_cast<size_t>(my_r0) * 2 + h) * kFft;
-                        pf_valid = nxt != nullptr;
-                        if (pf_valid && lane == 0) {
-                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                            mbar_expect_tx(pf_bar + warp, kFft * sizeof(float2));
-                            bulk_g2s(tile, nxt, kFft * sizeof(float2), pf_bar + warp);
-                        }
-                    }
                 }
                 Peak t;
                 float fsum;
@@ -522,8 +483,7 @@ size_t spectra_smem_bytes(int s) {
     return (static_cast<size_t>(s) * kFft + spec_warps(s) * kTileF2 + kCarrierTable) * sizeof(float2);
 }
 size_t correlate_smem_bytes(int np) {
-    return (4 * static_cast<size_t>(kFft) + 2 * np * kTileF2) * sizeof(float2) + 2 * np * sizeof(PairPartial) + 16 +
-           2 * np * sizeof(uint64_t);
+    return (4 * static_cast<size_t>(kFft) + 2 * np * kTileF2) * sizeof(float2) + 2 * np * sizeof(PairPartial) + 16;
 }
 
 bool spectra_supports(int s) {
