@@ -233,6 +233,9 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
             mbar_wait(mbar, parity);
             parity ^= 1;
             cur_prn = prn;
+            // De-phase the pairs after the CTA-wide barrier: warps that restart in step convoy on the shared-memory
+            // pipe (measured: -4 % on config 2, neutral elsewhere; profiles/ablation_r1.md).
+            __nanosleep(pair * 300);
         }
 
         if (active) {
