@@ -48,7 +48,7 @@ def alg_bytes_per_block() -> float:
 
 def make_ring(n_blocks: int, seed: int) -> np.ndarray:
     """complex64[n_blocks, N]: seeded gaussian noise with four planted satellites."""
-    from oracle import gypsum_oracle as o  # synthetic-input generator only (shared so CPU and GPU legs see the same bytes)
+    from gypsum_b200 import synth as o  # product-side generator (the oracle is only used by the CPU legs below)
 
     rng = np.random.default_rng(seed)
     ring = np.empty((n_blocks, N), dtype=np.complex64)
@@ -117,7 +117,7 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 def _cpu_block_worker(args):
     block, svs = args
-    from oracle import gypsum_oracle as o
+    from oracle import gypsum_oracle as o  # the CPU legs are the one place bench.py may execute the oracle
 
     return o.grid_cells(block, FS, N, svs, list(DOPPLERS))[0].sum()
 

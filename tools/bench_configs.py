@@ -15,8 +15,8 @@ import torch  # noqa: E402
 
 from gypsum_b200 import _native  # noqa: E402
 from gypsum_b200.gps_ca_prn_codes import ca_code_chips  # noqa: E402
-from oracle import gypsum_oracle as o  # noqa: E402  (synthetic input only)
-from oracle import tracker_oracle as to  # noqa: E402
+from gypsum_b200 import synth as o  # noqa: E402
+from gypsum_b200 import synth as to  # noqa: E402
 
 quick = "--quick" in sys.argv
 CHIPS = np.stack([ca_code_chips(sv) for sv in range(1, 33)]).astype(np.uint8)

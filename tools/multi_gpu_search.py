@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 from gypsum_b200 import _native  # noqa: E402
 from gypsum_b200.distributed import ShardedGridSearch  # noqa: E402
 from gypsum_b200.gps_ca_prn_codes import ca_code_chips  # noqa: E402
-from oracle import gypsum_oracle as o  # noqa: E402
+from gypsum_b200 import synth as o  # noqa: E402
 
 rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(local)

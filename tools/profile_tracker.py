@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from gypsum_b200 import _native  # noqa: E402
 from gypsum_b200.gps_ca_prn_codes import ca_code_chips  # noqa: E402
-from oracle import tracker_oracle as to  # noqa: E402
+from gypsum_b200 import synth as to  # noqa: E402
 
 n, fs, n_ch, n_ms = 2046, 2046000, 32, 300
 eng = _native.Engine(fs, n)

@@ -9,8 +9,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from gypsum_b200 import _native  # noqa: E402
 from gypsum_b200.gps_ca_prn_codes import ca_code_chips  # noqa: E402
-from oracle import gypsum_oracle as o  # noqa: E402
-from oracle import tracker_oracle as to  # noqa: E402
+from gypsum_b200 import synth as o  # noqa: E402
+from gypsum_b200 import synth as to  # noqa: E402
 
 chips = np.stack([ca_code_chips(sv) for sv in range(1, 33)]).astype(np.uint8)
 for n, m in ((2046, 2), (4092, 1)):
