@@ -1,4 +1,6 @@
 #!/bin/bash
+# Needs the experiment builds abl_a1.so .. abl_a3.so in the repo root: kernels.cu / warp_fft.cuh compiled with
+# -DGB_ABLATE=1..3 around the hooks described in profiles/ablation_r1.md (the hooks are not kept in the product source).
 # timing-only ablations of correlate_cells (results are wrong by construction): a1 = no pair exchange / barriers /
 # recombination twiddles, a2 = a1 + no replica-spectrum product, a3 = a2 + no tw1 table loads
 for a in base a1 a2 a3; do
