@@ -103,6 +103,7 @@ struct gb200_engine {
     int64_t launches = 0;
     size_t spec_budget_bytes = 80u << 20;
     int np_override = 0, rsplit_override = 0;
+    int w2048 = 12;  // one-warp-per-transform correlate kernel: warps per CTA for single-ms searches (0 = use the pair kernel)
     bool timing = false;
     int fused = -1;  // acquire_cells kernel choice: -1 automatic, 0 doppler_spectra + correlate_cells, 1 fused block-per-cell
     bool detect_fused = true;  // gb200_detect: fused block-per-cell kernel (every cell has its own Doppler)
@@ -209,6 +210,13 @@ int pick_rsplit(const gb200_engine* e, int np, long long n_cells) {
     return gcd_int(e->s, np);
 }
 
+// Non-coherent, record-only launches can use the one-warp-per-transform kernel: returns its warps per CTA or 0.
+int pick_w2048(const gb200_engine* e, int M, int kind, bool profile) {
+    if (e->w2048 <= 0 || kind != GB200_NON_COHERENT || profile) return 0;
+    if (M == 1) return (e->w2048 == 10 || e->w2048 == 12) ? e->w2048 : 12;
+    return 8;
+}
+
 // Warp pairs per CTA: 10 (20 warps / SM) for single-millisecond non-coherent searches, 8 otherwise (the
 // multi-millisecond accumulators need the larger register budget).  GB200_NP=8 forces the 8-pair build.
 int pick_np(const gb200_engine* e, int M, int kind, bool profile) {
@@ -265,7 +273,8 @@ int run_grid(gb200_engine* e, int n_blocks, int M, const int32_t* prn_idx, int P
     nb = std::min(nb, n_blocks);
     GB_CUDA(e, e->spec.ensure(per_block * nb));
 
-    const int np = pick_np(e, M, kind, false);
+    const int nw = pick_w2048(e, M, kind, false);
+    const int np = nw ? nw : pick_np(e, M, kind, false);  // CTA "slots": warps (one-warp kernel) or warp pairs
     const int rsplit = pick_rsplit(e, np, static_cast<long long>(nb) * P * D);
     const int cpg = np / rsplit;
     const int chunks = (D + cpg - 1) / cpg;
@@ -312,7 +321,8 @@ int run_grid(gb200_engine* e, int n_blocks, int M, const int32_t* prn_idx, int P
         const int grid = std::min(ca.n_groups, e->num_sms);
         {
             TimedLaunch tl(e, 1);
-            GB_CUDA(e, launch_correlate_cells(ca, np, grid, e->stream));
+            if (nw) GB_CUDA(e, launch_correlate_w2048(ca, nw, grid, e->stream));
+            else GB_CUDA(e, launch_correlate_cells(ca, np, grid, e->stream));
         }
         e->launches++;
     }
@@ -381,7 +391,8 @@ int run_cells(gb200_engine* e, int n_cells, const int32_t* prn_idx, const double
         return GB200_OK;
     }
 
-    const int np = pick_np(e, M, kind, profile_dev != nullptr);
+    const int nw = pick_w2048(e, M, kind, profile_dev != nullptr);
+    const int np = nw ? nw : pick_np(e, M, kind, profile_dev != nullptr);
     const int rsplit = pick_rsplit(e, np, n_cells);
     const int cpg = np / rsplit;
     std::vector<int> order(n_cells);
@@ -487,7 +498,8 @@ int run_cells(gb200_engine* e, int n_cells, const int32_t* prn_idx, const double
         const int grid = std::min(ng, e->num_sms);
         {
             TimedLaunch tl(e, 1);
-            GB_CUDA(e, launch_correlate_cells(ca, np, grid, e->stream));
+            if (nw) GB_CUDA(e, launch_correlate_w2048(ca, nw, grid, e->stream));
+            else GB_CUDA(e, launch_correlate_cells(ca, np, grid, e->stream));
         }
         e->launches++;
         c0 = c1;
@@ -546,6 +558,7 @@ int gb200_create(int device, int fs, int n, gb200_engine** out) {
     e->s = n / kChips;
     e->spec_budget_bytes = static_cast<size_t>(env_int("GB200_SPEC_BUDGET_MB", 80)) << 20;
     e->np_override = env_int("GB200_NP", 0);
+    e->w2048 = env_int("GB200_W2048", 12);
     e->rsplit_override = env_int("GB200_RSPLIT", 0);
     e->detect_fused = env_int("GB200_DETECT_FUSED", 1) != 0;
     auto fail = [&](cudaError_t c, const char* what) {
@@ -736,7 +749,8 @@ int gb200_detect(gb200_engine* e, int n_sv, const int32_t* prn_idx, int n_ms, gb
 
     const int MAXB = kRefineMaxBins;
     const int n_cells = n_sv * MAXB;
-    const int np = pick_np(e, n_ms, GB200_NON_COHERENT, false);
+    const int nw = pick_w2048(e, n_ms, GB200_NON_COHERENT, false);
+    const int np = nw ? nw : pick_np(e, n_ms, GB200_NON_COHERENT, false);
     const int rsplit = pick_rsplit(e, np, n_cells);
     const int cpg = np / rsplit;
     const int gps = (MAXB + cpg - 1) / cpg;  // groups per satellite
@@ -884,7 +898,8 @@ int gb200_detect(gb200_engine* e, int n_sv, const int32_t* prn_idx, int n_ms, gb
             ca.cell_gate = e->r_doppler.p;
             {
                 TimedLaunch tl(e, 1);
-                GB_CUDA(e, launch_correlate_cells(ca, np, std::min(ca.n_groups, e->num_sms), e->stream));
+                if (nw) GB_CUDA(e, launch_correlate_w2048(ca, nw, std::min(ca.n_groups, e->num_sms), e->stream));
+                else GB_CUDA(e, launch_correlate_cells(ca, np, std::min(ca.n_groups, e->num_sms), e->stream));
             }
             e->launches++;
         }

@@ -380,6 +380,184 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// correlate_cells, one warp per transform (non-coherent searches).  Same cell / group bookkeeping as above, but a
+// single warp owns a whole (cell, polyphase branch): it loads both half-spectra, multiplies by the replica spectrum
+// and runs the pruned inverse FFT-2048 of warp_fft.cuh (two FFT-32, 64x32 transpose, one FFT-64 per thread).  Per
+// transform pair this moves 40 KB through the shared-memory pipe instead of 52 KB and needs no partner warp: no
+// exchange tile, no pair barriers, no recombination twiddles, half the twiddle-table reads.
+// ---------------------------------------------------------------------------------------------------------
+template <int NW, bool SINGLE_MS>
+__global__ void __launch_bounds__(NW * 32, 1) k_correlate_w2048(const CorrelateArgs a) {
+    extern __shared__ __align__(16) float2 smem[];
+    float2* crep_s = smem;              // [2][1024]
+    float2* tw1_s = crep_s + 2 * kFft;  // [32][32]
+    float2* tiles = tw1_s + kFft;       // [NW][kTile64F2]
+    PairPartial* partial = reinterpret_cast<PairPartial*>(tiles + NW * kTile64F2);  // [NW]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(partial + NW);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float2* tile = tiles + warp * kTile64F2;
+
+    uint32_t parity = 0;
+    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(mbar, kFft * sizeof(float2));
+        bulk_g2s(tw1_s, a.tw1, kFft * sizeof(float2), mbar);
+    }
+    mbar_wait(mbar, parity);
+    parity ^= 1;
+
+    const int cells_per_group = NW / a.rsplit;
+    const int r_per_warp = a.s / a.rsplit;
+    const int my_cell = warp / a.rsplit;
+    const int my_r0 = (warp % a.rsplit) * r_per_warp;
+    const size_t unit_stride = static_cast<size_t>(a.M) * a.s * 2 * kFft;
+    int cur_prn = -1;
+
+    const int g0 = static_cast<int>(static_cast<long long>(blockIdx.x) * a.n_groups / gridDim.x);
+    const int g1 = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * a.n_groups / gridDim.x);
+    int gb = 0, gpl = 0, gch = 0;
+    if (a.grid_mode && g0 < g1) {
+        const int per_block = a.P * a.chunks;
+        gb = g0 / per_block;
+        const int rem = g0 - gb * per_block;
+        gpl = rem / a.chunks;
+        gch = rem - gpl * a.chunks;
+    }
+
+    for (int g = g0; g < g1; ++g) {
+        int prn, n_cells, unit = 0, out = 0;
+        if (a.grid_mode) {
+            prn = a.prn_idx[gpl];
+            n_cells = min(cells_per_group, a.D - gch * cells_per_group);
+            const int d = gch * cells_per_group + my_cell;
+            unit = gb * a.D + d;
+            out = (gb * a.P + gpl) * a.D + d;
+            if (++gch == a.chunks) {
+                gch = 0;
+                if (++gpl == a.P) {
+                    gpl = 0;
+                    ++gb;
+                }
+            }
+        } else {
+            prn = a.grp_prn[g];
+            n_cells = a.grp_count[g];
+            if (my_cell < n_cells) {
+                const int c = a.grp_first[g] + my_cell;
+                unit = a.cell_u[c];
+                out = a.cell_out[c];
+            }
+        }
+        bool active = my_cell < n_cells;
+        if (active && a.cell_gate) active = !isnan(a.cell_gate[out]);
+
+        if (prn != cur_prn) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(mbar, 2 * kFft * sizeof(float2));
+                bulk_g2s(crep_s, a.crep + static_cast<size_t>(prn) * 2 * kFft, 2 * kFft * sizeof(float2), mbar);
+            }
+            mbar_wait(mbar, parity);
+            parity ^= 1;
+            cur_prn = prn;
+            __nanosleep(warp * 150);  // de-phase the warps after the CTA-wide barrier
+        }
+
+        if (active) {
+            Peak pk;
+            peak_init(pk);
+            const float2* __restrict__ spec_u = a.spec + static_cast<size_t>(unit) * unit_stride;
+            for (int r = my_r0; r < my_r0 + r_per_warp; ++r) {
+                float acc[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) acc[k] = 0.f;
+                const int n_iter = SINGLE_MS ? 1 : a.M;
+                for (int it = 0; it < n_iter; ++it) {
+                    const float2* __restrict__ p = spec_u + static_cast<size_t>(it * a.s + r) * 2 * kFft;
+                    {
+                        float hr[32], hi[32];
+                        load_mul_vec(hr, hi, lane, p, crep_s);  // even bins
+                        w2048_phase1<0>(hi, hr, lane, tw1_s, tile);  // inverse = forward on swapped re/im
+                    }
+                    {
+                        float hr[32], hi[32];
+                        load_mul_vec(hr, hi, lane, p + kFft, crep_s + kFft);  // odd bins
+                        w2048_phase1<1>(hi, hr, lane, tw1_s, tile);
+                    }
+                    __syncwarp();
+                    float re[64], im[64];
+                    w2048_phase2(im, re, lane, tile);
+                    __syncwarp();  // the tile may be overwritten by the next transform
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) acc[k] += gb_sqrt(re[k] * re[k] + im[k] * im[k]);
+                }
+                // lags q = lane + 32 k: k < 16 and k >= 16 are the two halves thread_peak16 knows as h = 0 / 1
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    float v[16];
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) v[jj] = acc[16 * hh + jj];
+                    Peak t;
+                    float fsum;
+                    thread_peak16(v, lane, hh, a.s, r, t, fsum);
+                    t.sum = static_cast<double>(fsum);
+                    peak_merge(pk, t);
+                }
+            }
+            warp_reduce_peak(pk);
+            if (lane == 0) {
+                if (a.rsplit == 1) {
+                    CellRecord rec;
+                    rec.peak = pk.mx;
+                    rec.argmax = pk.idx;
+                    rec.sum = pk.sum;
+                    rec.count = pk.cnt;
+                    rec.probe_re = rec.probe_im = 0.f;
+                    rec.pad_ = 0;
+                    a.records[out] = rec;
+                } else {
+                    PairPartial pp;
+                    pp.mx = pk.mx;
+                    pp.idx = pk.idx;
+                    pp.cnt = pk.cnt;
+                    pp.sum = pk.sum;
+                    pp.pr_re = pp.pr_im = 0.f;
+                    pp.pad = 0;
+                    partial[warp] = pp;
+                }
+            }
+        }
+        if (a.rsplit != 1) {
+            __syncthreads();
+            if (active && (warp % a.rsplit) == 0 && lane == 0) {
+                Peak m;
+                peak_init(m);
+                for (int w = 0; w < a.rsplit; ++w) {
+                    const PairPartial pp = partial[warp + w];
+                    Peak o;
+                    o.mx = pp.mx;
+                    o.idx = pp.idx;
+                    o.cnt = pp.cnt;
+                    o.sum = pp.sum;
+                    peak_merge(m, o);
+                }
+                CellRecord rec;
+                rec.peak = m.mx;
+                rec.argmax = m.idx;
+                rec.sum = m.sum;
+                rec.count = m.cnt;
+                rec.probe_re = rec.probe_im = 0.f;
+                rec.pad_ = 0;
+                a.records[out] = rec;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // On-device Doppler refinement: the control flow of acquisition.py:70-152 without host round trips.  The
 // correlation work of every pass still runs in doppler_spectra / correlate_cells; these kernels only plan the
 // next pass's bins and apply the reference's selection rules.
@@ -489,6 +667,10 @@ size_t correlate_smem_bytes(int np) {
     return (4 * static_cast<size_t>(kFft) + 2 * np * kTileF2) * sizeof(float2) + 2 * np * sizeof(PairPartial) + 16;
 }
 
+size_t correlate_w2048_smem_bytes(int nw) {
+    return (3 * static_cast<size_t>(kFft) + static_cast<size_t>(nw) * kTile64F2) * sizeof(float2) + nw * sizeof(PairPartial) + 16;
+}
+
 bool spectra_supports(int s) {
     switch (s) {
         case 1: case 2: case 3: case 4: case 5: case 6: case 8: case 10: case 12: case 16: return true;
@@ -517,7 +699,15 @@ cudaError_t configure_kernels() {
     GB_ATTR(1) GB_ATTR(2) GB_ATTR(3) GB_ATTR(4) GB_ATTR(5) GB_ATTR(6) GB_ATTR(8) GB_ATTR(10) GB_ATTR(12) GB_ATTR(16)
 #undef GB_ATTR
     if ((e = correlate_attr<8>()) != cudaSuccess) return e;
-    return correlate_attr<10>();
+    if ((e = correlate_attr<10>()) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_correlate_w2048<10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(correlate_w2048_smem_bytes(10)))) != cudaSuccess)
+        return e;
+    if ((e = cudaFuncSetAttribute(k_correlate_w2048<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(correlate_w2048_smem_bytes(12)))) != cudaSuccess)
+        return e;
+    return cudaFuncSetAttribute(k_correlate_w2048<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(correlate_w2048_smem_bytes(8)));
 }
 
 cudaError_t launch_init_tables(float2* tw1, float2* tw2, cudaStream_t st) {
@@ -552,6 +742,14 @@ static void correlate_dispatch(const CorrelateArgs& a, int grid, cudaStream_t st
         else k_correlate_cells<NP, 2, false><<<grid, NP * 64, sm, st>>>(a);
     }
 }
+// One-warp-per-transform build: nw = 10 warps needs M == 1 (the caller guarantees it), nw = 8 takes any M.
+cudaError_t launch_correlate_w2048(const CorrelateArgs& a, int nw, int grid, cudaStream_t st) {
+    if (nw == 12) k_correlate_w2048<12, true><<<grid, 384, correlate_w2048_smem_bytes(12), st>>>(a);
+    else if (nw == 10) k_correlate_w2048<10, true><<<grid, 320, correlate_w2048_smem_bytes(10), st>>>(a);
+    else k_correlate_w2048<8, false><<<grid, 256, correlate_w2048_smem_bytes(8), st>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_correlate_cells(const CorrelateArgs& a, int np, int grid, cudaStream_t st) {
     if (np == 10) correlate_dispatch<10>(a, grid, st);
     else correlate_dispatch<8>(a, grid, st);

@@ -107,6 +107,7 @@ cudaError_t launch_init_tables(float2* tw1, float2* tw2, cudaStream_t st);
 cudaError_t launch_replica_spectra(const uint8_t* chips_dev, int n_prn, float2* crep, cudaStream_t st);
 cudaError_t launch_doppler_spectra(const SpectraArgs& a, cudaStream_t st);
 cudaError_t launch_correlate_cells(const CorrelateArgs& a, int np, int grid, cudaStream_t st);
+cudaError_t launch_correlate_w2048(const CorrelateArgs& a, int nw, int grid, cudaStream_t st);
 cudaError_t configure_kernels();
 
 }  // namespace gb

@@ -309,3 +309,70 @@ GB_HD GB_INLINE void replica_spectrum_bin(const uint8_t* chips, int g, const dou
 }
 
 }  // namespace gb
+
+namespace gb {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// One-warp inverse FFT-2048 (pruned to the 1024 outputs a padded correlation needs).  n = l' + 64 j'' with
+// l' = 2*lane + h: a thread holds, for both bin parities h, the 32 elements Y_h[lane + 32 j''] -- exactly the
+// two half-spectra of the pair design, in the same memory layout -- so
+//     X[k1 + 32 k2] = sum_{l'} W64^(l' k2) * [ W2048^(l' k1) * sum_{j''} Y[l' + 64 j''] W32^(j'' k1) ]
+// is: two in-register FFT-32 (one per parity), twiddle W2048^((2 lane + h) k1) = tw1[k1][lane] * W2048^(h k1) (the
+// second factor is a compile-time constant), a 64x32 transpose through the warp's tile, one in-register FFT-64
+// over l' per thread (column k1 = lane) of which only outputs k2 < 32 are used.  Output: X[lane + 32 k2] -- the same lag
+// layout as before.  No partner warp, no exchange, no recombination twiddles.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kT64Stride = 33;                 // float2 per tile row: consecutive rows hit different banks
+constexpr int kTile64F2 = 64 * kT64Stride;     // 64 rows (l') x 32 columns (k1)
+
+// W2048^m, m = 0..31 (forward sign), for the odd-parity twiddle
+#define GB_W2048_TABLE                                                                                                  \
+    {1.000000000e+00f, 0.000000000e+00f}, {9.999952938e-01f, -3.067956763e-03f}, {9.999811753e-01f, -6.135884649e-03f},  \
+    {9.999576446e-01f, -9.203754782e-03f}, {9.999247018e-01f, -1.227153829e-02f}, {9.998823475e-01f, -1.533920628e-02f}, \
+    {9.998305818e-01f, -1.840672991e-02f}, {9.997694054e-01f, -2.147408028e-02f}, {9.996988187e-01f, -2.454122852e-02f}, \
+    {9.996188225e-01f, -2.760814578e-02f}, {9.995294175e-01f, -3.067480318e-02f}, {9.994306046e-01f, -3.374117185e-02f}, \
+    {9.993223846e-01f, -3.680722294e-02f}, {9.992047586e-01f, -3.987292759e-02f}, {9.990777278e-01f, -4.293825693e-02f}, \
+    {9.989412932e-01f, -4.600318213e-02f}, {9.987954562e-01f, -4.906767433e-02f}, {9.986402182e-01f, -5.213170468e-02f}, \
+    {9.984755806e-01f, -5.519524435e-02f}, {9.983015449e-01f, -5.825826450e-02f}, {9.981181129e-01f, -6.132073630e-02f}, \
+    {9.979252862e-01f, -6.438263093e-02f}, {9.977230666e-01f, -6.744391956e-02f}, {9.975114561e-01f, -7.050457339e-02f}, \
+    {9.972904567e-01f, -7.356456360e-02f}, {9.970600703e-01f, -7.662386139e-02f}, {9.968202993e-01f, -7.968243797e-02f}, \
+    {9.965711458e-01f, -8.274026455e-02f}, {9.963126122e-01f, -8.579731234e-02f}, {9.960447009e-01f, -8.885355258e-02f}, \
+    {9.957674145e-01f, -9.190895650e-02f}, {9.954807555e-01f, -9.496349533e-02f}
+
+// Phase 1 for one parity h: re/im[j] = Y_h[lane + 32 j].  tw1 is the W1024^(lane k1) table (pair-interleaved).
+template <int H>
+GB_HD GB_INLINE void w2048_phase1(float (&re)[32], float (&im)[32], int lane, const float2* tw1, float2* tile) {
+    constexpr float kW[32][2] = {GB_W2048_TABLE};
+    fft32_fwd(re, im);
+    float2* row = tile + (H * 32 + lane) * kT64Stride;  // physical row of l' = 2*lane + H
+#pragma unroll
+    for (int kp = 0; kp < 16; ++kp) {
+        float2 w0, w1;
+        ld_pair(tw1 + 2 * (kp * 32 + lane), w0, w1);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int k1 = 2 * kp + q;
+            float2 w = q ? w1 : w0;
+            if (H == 1) w = make_float2(w.x * kW[k1][0] - w.y * kW[k1][1], w.x * kW[k1][1] + w.y * kW[k1][0]);
+            if (k1 == 0 && H == 0) row[0] = make_float2(re[0], im[0]);
+            else row[k1] = make_float2(re[k1] * w.x - im[k1] * w.y, re[k1] * w.y + im[k1] * w.x);
+        }
+    }
+}
+
+// Phase 2: thread `lane` owns column k1 = lane: gathers the 64 rows (l' natural order), FFT-64 over l'.
+// Afterwards re/im[k2] = X[lane + 32 k2]; only k2 < 32 are meaningful for the pruned transform.
+GB_HD GB_INLINE void w2048_phase2(float (&re)[64], float (&im)[64], int lane, const float2* tile) {
+#pragma unroll
+    for (int p = 0; p < 32; ++p) {
+        const float2 e = tile[p * kT64Stride + lane];         // l' = 2p
+        const float2 o = tile[(32 + p) * kT64Stride + lane];  // l' = 2p + 1
+        re[2 * p] = e.x;
+        im[2 * p] = e.y;
+        re[2 * p + 1] = o.x;
+        im[2 * p + 1] = o.y;
+    }
+    fft64_fwd(re, im);
+}
+
+}  // namespace gb

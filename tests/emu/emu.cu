@@ -214,3 +214,26 @@ void emu_track_update(TrackState* st, const float* elp /* E.re E.im L.re L.im P.
                  t0, fs, *out);
 }
 }
+
+// ---- one-warp pruned inverse FFT-2048 (w2048_phase1/2) ----
+extern "C" void emu_ifft2048_pruned(const float2* y_even, const float2* y_odd, float2* out /*[1024]*/) {
+    init_tables();
+    std::vector<float2> tile(kTile64F2);
+    static float ra[32][32], ia[32][32], rb[32][32], ib[32][32];
+    for (int lane = 0; lane < 32; ++lane)
+        for (int j = 0; j < 32; ++j) {
+            ra[lane][j] = y_even[lane + 32 * j].x;
+            ia[lane][j] = y_even[lane + 32 * j].y;
+            rb[lane][j] = y_odd[lane + 32 * j].x;
+            ib[lane][j] = y_odd[lane + 32 * j].y;
+        }
+    for (int lane = 0; lane < 32; ++lane) {  // inverse = forward on swapped re/im
+        w2048_phase1<0>(ia[lane], ra[lane], lane, g_tw1.data(), tile.data());
+        w2048_phase1<1>(ib[lane], rb[lane], lane, g_tw1.data(), tile.data());
+    }
+    for (int lane = 0; lane < 32; ++lane) {
+        float re[64], im[64];
+        w2048_phase2(im, re, lane, tile.data());
+        for (int k2 = 0; k2 < 32; ++k2) out[lane + 32 * k2] = make_float2(re[k2], im[k2]);
+    }
+}

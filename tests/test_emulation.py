@@ -42,3 +42,17 @@ def test_polyphase_correlation_matches_oracle(emu_lib, n, n_ms, sv, f):
     emu_lib.emu_cell_profile(iq.ctypes.data, n, n_ms, float(fs), float(f), chips.ctypes.data, 1, co.ctypes.data, None)
     refc = o.integrate(o.COHERENT, iq, fs, n, f, prn)
     assert np.abs(co - refc).max() <= 1e-6 * np.abs(refc).max()
+
+
+def test_one_warp_pruned_ifft2048(emu_lib):
+    """w2048_phase1/2: out[k] = sum_g Y[g] exp(+2 pi i g k / 2048) for k < 1024, Y[2f+h] = Y_h[f]."""
+    rng = np.random.default_rng(5)
+    ye = (rng.standard_normal(1024) + 1j * rng.standard_normal(1024)).astype(np.complex64)
+    yo = (rng.standard_normal(1024) + 1j * rng.standard_normal(1024)).astype(np.complex64)
+    out = np.zeros(1024, np.complex64)
+    emu_lib.emu_ifft2048_pruned(ye.ctypes.data_as(ctypes.c_void_p), yo.ctypes.data_as(ctypes.c_void_p),
+                                out.ctypes.data_as(ctypes.c_void_p))
+    y = np.empty(2048, complex)
+    y[0::2], y[1::2] = ye, yo
+    ref = (np.fft.ifft(y) * 2048)[:1024]
+    assert np.abs(out - ref).max() <= 5e-7 * np.abs(ref).max()
