@@ -328,7 +328,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
                     "d2h_bytes_per_step": B * n_cells * 32, "single_block_latency_us": single_us},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_correlate_cells", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_correlate_w2048 (correlate_cells, one warp per transform)", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                          "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg, "kernel_ms_per_launch": corr_ms,
                          "kernel_share_of_step": k_corr_ms / max(k_corr_ms + k_spec_ms, 1e-12),
