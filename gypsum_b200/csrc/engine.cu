@@ -280,9 +280,9 @@ int run_grid(gb200_engine* e, int n_blocks, int M, const int32_t* prn_idx, int P
     const int np = nw ? nw : pick_np(e, M, kind, false);  // CTA "slots": warps (one-warp kernel) or warp pairs
     const int rsplit = pick_rsplit(e, np, static_cast<long long>(nb) * P * D);
     const int cpg = np / rsplit;
-    const int chunks = (D + cpg - 1) / cpg;
     for (int b0 = 0; b0 < n_blocks; b0 += nb) {
         const int nbb = std::min(nb, n_blocks - b0);
+        const int chunks = (nbb * D + cpg - 1) / cpg;  // groups per PRN: its nbb*D cells in chunks of cpg
         SpectraArgs sa{};
         sa.iq = e->iq + static_cast<size_t>(b0) * M * e->N;
         sa.doppler = e->d_doppler.p;
@@ -314,10 +314,11 @@ int run_grid(gb200_engine* e, int n_blocks, int M, const int32_t* prn_idx, int P
         ca.M = M;
         ca.kind = kind;
         ca.rsplit = rsplit;
-        ca.n_groups = nbb * P * chunks;
+        ca.n_groups = P * chunks;
         ca.grid_mode = 1;
         ca.P = P;
         ca.D = D;
+        ca.n_blocks = nbb;
         ca.chunks = chunks;
         ca.prn_idx = e->d_ints.p;
         ca.cell_probe = nullptr;

@@ -186,30 +186,28 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
     // re-staged only when the PRN changes, and the (block, prn, chunk) decode is incremental.
     const int g0 = static_cast<int>(static_cast<long long>(blockIdx.x) * a.n_groups / gridDim.x);
     const int g1 = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * a.n_groups / gridDim.x);
-    int gb = 0, gpl = 0, gch = 0;
+    // grid mode: groups are ordered (PRN, chunk of the PRN's n_blocks*D cells), so a CTA's contiguous range stays on
+    // one PRN for many groups and only the last chunk of a PRN is partly filled
+    int gpl = 0, gch = 0;
     if (a.grid_mode && g0 < g1) {
-        const int per_block = a.P * a.chunks;
-        gb = g0 / per_block;
-        const int rem = g0 - gb * per_block;
-        gpl = rem / a.chunks;
-        gch = rem - gpl * a.chunks;
+        gpl = g0 / a.chunks;
+        gch = g0 - gpl * a.chunks;
     }
+    const int cells_per_prn = a.n_blocks * a.D;
 
     for (int g = g0; g < g1; ++g) {
         // ---- decode the group (uniform across the CTA) ----
         int prn, n_cells, unit = 0, out = 0;
         if (a.grid_mode) {
             prn = a.prn_idx[gpl];
-            n_cells = min(cells_per_group, a.D - gch * cells_per_group);
-            const int d = gch * cells_per_group + my_cell;
-            unit = gb * a.D + d;
-            out = (gb * a.P + gpl) * a.D + d;
+            n_cells = min(cells_per_group, cells_per_prn - gch * cells_per_group);
+            const int c = gch * cells_per_group + my_cell;  // flat (block, doppler) index within this PRN
+            const int b = c / a.D, d = c - b * a.D;
+            unit = c;  // = b * D + d
+            out = (b * a.P + gpl) * a.D + d;
             if (++gch == a.chunks) {
                 gch = 0;
-                if (++gpl == a.P) {
-                    gpl = 0;
-                    ++gb;
-                }
+                ++gpl;
             }
         } else {
             prn = a.grp_prn[g];
@@ -417,29 +415,27 @@ __global__ void __launch_bounds__(NW * 32, 1) k_correlate_w2048(const CorrelateA
 
     const int g0 = static_cast<int>(static_cast<long long>(blockIdx.x) * a.n_groups / gridDim.x);
     const int g1 = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * a.n_groups / gridDim.x);
-    int gb = 0, gpl = 0, gch = 0;
+    // grid mode: groups are ordered (PRN, chunk of the PRN's n_blocks*D cells), so a CTA's contiguous range stays on
+    // one PRN for many groups and only the last chunk of a PRN is partly filled
+    int gpl = 0, gch = 0;
     if (a.grid_mode && g0 < g1) {
-        const int per_block = a.P * a.chunks;
-        gb = g0 / per_block;
-        const int rem = g0 - gb * per_block;
-        gpl = rem / a.chunks;
-        gch = rem - gpl * a.chunks;
+        gpl = g0 / a.chunks;
+        gch = g0 - gpl * a.chunks;
     }
+    const int cells_per_prn = a.n_blocks * a.D;
 
     for (int g = g0; g < g1; ++g) {
         int prn, n_cells, unit = 0, out = 0;
         if (a.grid_mode) {
             prn = a.prn_idx[gpl];
-            n_cells = min(cells_per_group, a.D - gch * cells_per_group);
-            const int d = gch * cells_per_group + my_cell;
-            unit = gb * a.D + d;
-            out = (gb * a.P + gpl) * a.D + d;
+            n_cells = min(cells_per_group, cells_per_prn - gch * cells_per_group);
+            const int c = gch * cells_per_group + my_cell;  // flat (block, doppler) index within this PRN
+            const int b = c / a.D, d = c - b * a.D;
+            unit = c;  // = b * D + d
+            out = (b * a.P + gpl) * a.D + d;
             if (++gch == a.chunks) {
                 gch = 0;
-                if (++gpl == a.P) {
-                    gpl = 0;
-                    ++gb;
-                }
+                ++gpl;
             }
         } else {
             prn = a.grp_prn[g];

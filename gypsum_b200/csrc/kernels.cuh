@@ -32,7 +32,7 @@ struct CorrelateArgs {
     int rsplit;          // pairs cooperating on one cell (divides s and NP)
     int n_groups;
     // grid mode (cells = blocks x prn list x doppler list)
-    int grid_mode, P, D, chunks;  // chunks = ceil(D / cells_per_group)
+    int grid_mode, P, D, n_blocks, chunks;  // chunks = ceil(n_blocks * D / cells_per_group): groups per PRN
     const int* prn_idx;           // [P]
     // list mode (cells sorted by PRN)
     const int* grp_first;
