@@ -3,9 +3,12 @@
 // bulk copies, carrier wipe-off, forward warp FFTs, product with conj(FFT(replica)), inverse warp FFTs, |.|
 // (or complex) accumulation over the milliseconds in registers, warp-reduced peak.
 //
-// It exists to be measured against the de-duplicated pair doppler_spectra + correlate_cells:
-// the forward half of the pipeline does not depend on the PRN, so on a 32-PRN grid this kernel redoes every wipe-off
-// and forward transform 32 times.  The engine uses it only when asked to (gb200_set_fused); parity tests run both.
+// Against the de-duplicated pair doppler_spectra + correlate_cells: the forward half of the
+// pipeline does not depend on the PRN, so on a 32-PRN x shared-Doppler grid this kernel redoes every wipe-off and forward
+// transform 32 times and loses ~3x; when every cell has its own Doppler (the refinement passes of
+// acquisition.py:81-101) nothing can be shared and it wins ~2x because nothing round-trips through HBM.  The engine
+// therefore uses it in gb200_detect and, by automatic choice, for cell lists with mostly distinct Dopplers
+// (gb200_set_fused overrides); grids always run the split pair.  Parity tests run both.
 #include "kernels.cuh"
 #include "ptx_helpers.cuh"
 #include "warp_fft.cuh"

@@ -6,8 +6,11 @@
 //                     bin and shared by all PRNs instead of being redone per cell as the reference does.
 //   correlate_cells   per (PRN, Doppler) cell: x conj(FFT(replica)) (utils.py:69, spectrum staged into shared
 //                     memory with a TMA bulk copy), inverse warp FFTs (utils.py:73), |.| accumulation over ms
-//                     (utils.py:102-104) in registers, peak/argmax/sum/count reduction with warp shuffles
-//                     (acquisition.py:181-189, utils.py:111-116).
+//                     (utils.py:102-104) in registers, peak/argmax/sum/count reduction with REDUX / warp shuffles
+//                     (acquisition.py:181-189, utils.py:111-116).  Two builds: k_correlate_cells (a warp pair per
+//                     transform pair; multi-ms, coherent, profile) and k_correlate_w2048 (one warp per pruned
+//                     inverse FFT-2048; single-ms searches).
+//   refine_*          planning / selection kernels of the on-device search (acquisition.py:70-152).
 #include "kernels.cuh"
 #include "ptx_helpers.cuh"
 #include "warp_fft.cuh"
