@@ -72,3 +72,63 @@ class ShardedGridSearch:
             rr = shard_range(prn_idx.size, r, self.world)
             full[:, rr.start:rr.stop] = g[r][:, :len(rr)]
         return full
+
+
+class ShardedBlockSearch:
+    """Many independent blocks (BASELINE config 5: 1000 x 1-ms blocks over 8 GPUs): rank 0 holds the IQ, each rank
+    receives only its contiguous share of blocks (one scatter), searches the full PRN x Doppler grid on them, and the
+    per-cell records come back with one gather.  No collective between the two."""
+
+    def __init__(self, engine, device, group=None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.engine = engine
+        self.device = device
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def acquire_blocks(self, iq, n_blocks: int, ms_per_block: int, prn_idx, doppler_hz, kind: int):
+        """iq: complex64[n_blocks * ms_per_block * N] on rank 0 (ignored elsewhere).  Returns the record array
+        [n_blocks, n_prn, n_doppler] on rank 0 and None on the other ranks."""
+        import torch
+
+        from gypsum_b200._native import RECORD_DTYPE
+
+        prn = np.ascontiguousarray(prn_idx, dtype=np.int32)
+        dop = np.ascontiguousarray(doppler_hz, dtype=np.float64)
+        per_block = ms_per_block * self.engine.samples_per_ms * 2  # float32 words
+        shares = [shard_range(n_blocks, r, self.world) for r in range(self.world)]
+        most = max(len(s) for s in shares)
+        # one scatter of equal-sized (padded) shares
+        mine = torch.empty(most * per_block, dtype=torch.float32, device=self.device)
+        if self.rank == 0:
+            words = torch.from_numpy(np.ascontiguousarray(iq, dtype=np.complex64)[: n_blocks * per_block // 2].view(np.float32))
+            parts = []
+            for s in shares:
+                part = torch.zeros(most * per_block, dtype=torch.float32)
+                part[: len(s) * per_block] = words[s.start * per_block: s.stop * per_block]
+                parts.append(part.to(self.device))
+            self.dist.scatter(mine, parts, src=0, group=self.group)
+        else:
+            self.dist.scatter(mine, None, src=0, group=self.group)
+
+        my = shares[self.rank]
+        rec_bytes = most * prn.size * dop.size * RECORD_BYTES
+        out = torch.zeros(rec_bytes, dtype=torch.uint8, device=self.device)
+        if len(my):
+            self.engine.bind_iq_device(mine.data_ptr(), len(my) * per_block // 2)
+            self.engine.acquire_grid_device(len(my), ms_per_block, prn, dop, kind, out.data_ptr())
+            if str(self.device) != "cpu":
+                torch.cuda.current_stream().synchronize()
+        # one gather of the records
+        gathered = [torch.empty_like(out) for _ in range(self.world)] if self.rank == 0 else None
+        self.dist.gather(out, gathered, dst=0, group=self.group)
+        if self.rank != 0:
+            return None
+        full = np.empty((n_blocks, prn.size, dop.size), dtype=RECORD_DTYPE)
+        for r, s in enumerate(shares):
+            g = gathered[r].cpu().numpy().view(RECORD_DTYPE).reshape(most, prn.size, dop.size)
+            full[s.start:s.stop] = g[: len(s)]
+        return full

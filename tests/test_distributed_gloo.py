@@ -60,6 +60,48 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _block_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from gypsum_b200.distributed import ShardedBlockSearch
+    from oracle import gypsum_oracle as o
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    x = o.synth_iq(6, 2046, 5, 2046000, [(9, -500.0, 1234, 0.0, 0.4)]) if rank == 0 else None
+    search = ShardedBlockSearch(_OracleEngine(), "cpu")
+    full = search.acquire_blocks(x, 5, 1, np.array([8, 0]), [-500.0, 0.0], 2)
+    q.put((rank, None if full is None else (full["peak"].copy(), full["argmax"].copy())))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_block_search_scatter_and_gather(world):
+    """5 blocks over 2 / 3 ranks (uneven shares): one scatter of blocks, one gather of records, rank 0 gets the table
+    in block order."""
+    from oracle import gypsum_oracle as o
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_block_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(got[r] is None for r in range(1, world))
+    peak, arg = got[0]
+    x = o.synth_iq(6, 2046, 5, 2046000, [(9, -500.0, 1234, 0.0, 0.4)])
+    for b in range(5):
+        pk, ag, _, _ = o.grid_cells(x[b * 2046:(b + 1) * 2046], 2046000, 2046, [9, 1], [-500.0, 0.0])
+        assert np.allclose(peak[b], pk, rtol=1e-6) and np.array_equal(arg[b], ag)
+        assert arg[b, 0, 0] == 1234
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_sharded_grid_search_matches_single_process(world):
     from oracle import gypsum_oracle as o

@@ -12,7 +12,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from gypsum_b200 import _native  # noqa: E402
-from gypsum_b200.distributed import ShardedGridSearch  # noqa: E402
+from gypsum_b200.distributed import ShardedBlockSearch, ShardedGridSearch  # noqa: E402
 from gypsum_b200.gps_ca_prn_codes import ca_code_chips  # noqa: E402
 from gypsum_b200 import synth as o  # noqa: E402
 
@@ -48,4 +48,35 @@ for n, m in ((2046, 1), (4092, 10)):
                           "identical_to_single_gpu": bool(ok), "sv25": [float(dop[b]), int(full["argmax"][0, 24, b])]}), flush=True)
     eng.set_stream(0)
     eng.close()
+# config-5 shape: independent 1-ms blocks @ 16.368 Msps, 32 x 81 cells each, blocks scattered over the ranks
+n, m, nb = 16368, 1, 24
+fs = n * 1000
+eng = _native.Engine(fs, n, device=local)
+eng.set_replicas(np.stack([ca_code_chips(sv) for sv in range(1, 33)]).astype(np.uint8))
+st = torch.cuda.Stream()
+torch.cuda.set_stream(st)
+eng.set_stream(st.cuda_stream)
+dop = np.arange(-10000, 10001, 250.0)
+x = None
+if rank == 0:
+    rng = np.random.default_rng(3)
+    x = ((rng.standard_normal(n * nb, dtype=np.float32) + 1j * rng.standard_normal(n * nb, dtype=np.float32)) * np.float32(0.7071)).astype(np.complex64)
+    x[: n] += o.synth_iq(0, n, 1, fs, [(25, 1500.0, 7777, 0.3, 0.3)], sigma=0.0)
+search = ShardedBlockSearch(eng, torch.device("cuda", local))
+full = search.acquire_blocks(x, nb, m, np.arange(32), dop, _native.NON_COHERENT)
+torch.cuda.synchronize(); dist.barrier()
+import time
+t0 = time.perf_counter()
+full = search.acquire_blocks(x, nb, m, np.arange(32), dop, _native.NON_COHERENT)
+torch.cuda.synchronize(); dist.barrier()
+dt = time.perf_counter() - t0
+if rank == 0:
+    eng.upload_iq(x)
+    one = eng.acquire_grid(nb, m, np.arange(32), dop)
+    ok = all(np.array_equal(full[k], one[k]) for k in ("peak", "argmax", "count"))
+    b = int(np.argmax(full["peak"][0, 24]))
+    print(json.dumps({"workload": f"block-sharded search (scatter + gather), {nb} blocks @ 16.368 Msps, 32x81 cells", "world": world,
+                      "seconds_host_to_host": dt, "identical_to_single_gpu": bool(ok), "sv25": [float(dop[b]), int(full["argmax"][0, 24, b])]}), flush=True)
+eng.set_stream(0)
+eng.close()
 dist.destroy_process_group()
