@@ -164,3 +164,31 @@ def test_drop_in_tracker_class(engine):
     with pytest.raises(RuntimeError):
         GpsSatelliteTrackingParameters(satellite=sat, current_doppler_shift=0, current_carrier_wave_phase_shift=0,
                                        current_prn_code_phase_shift=0, doppler_shifts=[], carrier_wave_phases=[])
+
+
+def test_tracker_bank_class(engine):
+    """gypsum_b200.tracker.TrackerBank: channels given as (satellite, doppler, phase, code phase) like
+    pipeline.py:56-62 seeds them; one launch for the whole block of milliseconds == the per-millisecond drop-in."""
+    from gypsum_b200.antenna_sample_provider import AntennaSampleChunk
+    from gypsum_b200.gps_ca_prn_codes import GpsSatelliteId, generate_replica_prn_signals
+    from gypsum_b200.satellite import GpsSatellite
+    from gypsum_b200.tracker import GpsSatelliteTracker, GpsSatelliteTrackingParameters, TrackerBank
+
+    chans = [(25, 1500.3, 0.0, 777, 0.3, 0.004), (7, -2212.7, 0.0, 100, 1.0, 0.005)]
+    x = t.synth_tracking_iq(33, N, 40, FS, chans)
+    codes = generate_replica_prn_signals()
+    sats = {sv: GpsSatellite(GpsSatelliteId(sv), codes[GpsSatelliteId(sv)], 2) for sv in (25, 7)}
+    bank = TrackerBank([(sats[25], 1500.0, 0.0, 777), (sats[7], -2210.0, 0.5, 100)], Attrs())
+    rec = bank.process(x, times(40))
+    assert rec.shape == (2, 40)
+    for c, (sv, f0, p0, cp0) in enumerate([(25, 1500.0, 0.0, 777), (7, -2210.0, 0.5, 100)]):
+        params = GpsSatelliteTrackingParameters(satellite=sats[sv], current_doppler_shift=f0,
+                                                current_carrier_wave_phase_shift=p0, current_prn_code_phase_shift=cp0,
+                                                doppler_shifts=[])
+        trk = GpsSatelliteTracker(params, Attrs(), keep_correlation_profiles=False)
+        for k in range(40):
+            a, b = t.chunk_times(k, FS, N)
+            ps = trk.process_samples(AntennaSampleChunk(a, b, x[k * N:(k + 1) * N]))
+            assert ps.pseudosymbol.as_val() == rec[c, k]["symbol"]
+        assert params.current_doppler_shift == rec[c, -1]["doppler"]
+        assert len(params.non_coherent_correlation_profiles) == 0
