@@ -293,6 +293,16 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         eng.acquire_grid(1, N_MS, prn, dop, _native.NON_COHERENT)
         lat.append(time.perf_counter() - t1)
     single_us = 1e6 * float(np.median(lat[5:]))
+    # ... and one block per call with inputs resident (device time of K1 + K2 for a single 32x41 grid)
+    one_rec = torch.empty(n_cells * 32, dtype=torch.uint8, device="cuda")
+
+    def one_block_step(k: int) -> None:
+        eng.bind_iq_device(ring_dev.data_ptr() + (k % ring_blocks) * block_bytes, N)
+        eng.acquire_grid_device(1, N_MS, prn, dop, _native.NON_COHERENT, one_rec.data_ptr())
+
+    for k in range(5):
+        one_block_step(k)
+    one_block_ms = timed(one_block_step, 200, first=5) / 200
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -330,6 +340,9 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
             },
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": B * block_bytes,
                     "d2h_bytes_per_step": B * n_cells * 32, "single_block_latency_us": single_us},
+            "single_block": {"note": "the same grid with ONE 1-ms block per call (blocks_per_step = 1)",
+                             "device_Msamples_per_s": N / (one_block_ms * 1e-3) / 1e6 * world, "device_us_per_block": 1e3 * one_block_ms,
+                             "e2e_Msamples_per_s": N / (single_us * 1e-6) / 1e6 * world},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_correlate_w2048 (correlate_cells, one warp per transform)", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
