@@ -74,6 +74,9 @@ __global__ void __launch_bounds__(spec_warps(S) * 32) k_doppler_spectra(const Sp
 
     const int unit = blockIdx.x / a.M, i = blockIdx.x % a.M;
     const int b = unit / a.n_doppler, d = unit % a.n_doppler;
+    // Let the dependent grid (correlate_*) start its prologue as soon as every CTA of this grid has started; it still
+    // waits (griddepcontrol.wait) for this whole grid to finish before it reads the spectra.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const double f = a.doppler[d];
     if (isnan(f)) return;  // slot switched off by the on-device search planner
     const float2* __restrict__ src = a.iq + static_cast<size_t>(b) * a.block_stride + static_cast<size_t>(i) * a.N;
@@ -408,6 +411,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_correlate_w2048(const CorrelateA
     }
     mbar_wait(mbar, parity);
     parity ^= 1;
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // see k_correlate_cells: PDL against doppler_spectra
 
     const int cells_per_group = NW / a.rsplit;
     const int r_per_warp = a.s / a.rsplit;
@@ -729,23 +733,40 @@ cudaError_t launch_doppler_spectra(const SpectraArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// Launch as a programmatic dependent of the previous kernel in the stream (doppler_spectra): the grid may start its
+// prologue while the producer drains; it blocks at griddepcontrol.wait until the producer's writes are visible.
+template <class K>
+static void launch_dependent(K kernel, const CorrelateArgs& a, int grid, int block, size_t sm, cudaStream_t st) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = sm;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, a);
+}
+
 template <int NP>
 static void correlate_dispatch(const CorrelateArgs& a, int grid, cudaStream_t st) {
     const size_t sm = correlate_smem_bytes(NP);
     const bool prof = a.profile != nullptr;
     if (a.kind == kKindCoherent) {
-        if (prof) k_correlate_cells<NP, 1, true><<<grid, NP * 64, sm, st>>>(a);
-        else k_correlate_cells<NP, 1, false><<<grid, NP * 64, sm, st>>>(a);
+        if (prof) launch_dependent(k_correlate_cells<NP, 1, true>, a, grid, NP * 64, sm, st);
+        else launch_dependent(k_correlate_cells<NP, 1, false>, a, grid, NP * 64, sm, st);
     } else {
-        if (prof) k_correlate_cells<NP, 2, true><<<grid, NP * 64, sm, st>>>(a);
-        else k_correlate_cells<NP, 2, false><<<grid, NP * 64, sm, st>>>(a);
+        if (prof) launch_dependent(k_correlate_cells<NP, 2, true>, a, grid, NP * 64, sm, st);
+        else launch_dependent(k_correlate_cells<NP, 2, false>, a, grid, NP * 64, sm, st);
     }
 }
 // One-warp-per-transform build: nw = 10 warps needs M == 1 (the caller guarantees it), nw = 8 takes any M.
 cudaError_t launch_correlate_w2048(const CorrelateArgs& a, int nw, int grid, cudaStream_t st) {
-    if (nw == 12) k_correlate_w2048<12, true><<<grid, 384, correlate_w2048_smem_bytes(12), st>>>(a);
-    else if (nw == 10) k_correlate_w2048<10, true><<<grid, 320, correlate_w2048_smem_bytes(10), st>>>(a);
-    else k_correlate_w2048<8, false><<<grid, 256, correlate_w2048_smem_bytes(8), st>>>(a);
+    if (nw == 12) launch_dependent(k_correlate_w2048<12, true>, a, grid, 384, correlate_w2048_smem_bytes(12), st);
+    else if (nw == 10) launch_dependent(k_correlate_w2048<10, true>, a, grid, 320, correlate_w2048_smem_bytes(10), st);
+    else launch_dependent(k_correlate_w2048<8, false>, a, grid, 256, correlate_w2048_smem_bytes(8), st);
     return cudaGetLastError();
 }
 
