@@ -11,6 +11,8 @@
 //                     transform pair; multi-ms, coherent, profile) and k_correlate_w2048 (one warp per pruned
 //                     inverse FFT-2048; single-ms searches).
 //   refine_*          planning / selection kernels of the on-device search (acquisition.py:70-152).
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "ptx_helpers.cuh"
 #include "warp_fft.cuh"
@@ -74,9 +76,9 @@ __global__ void __launch_bounds__(spec_warps(S) * 32) k_doppler_spectra(const Sp
 
     const int unit = blockIdx.x / a.M, i = blockIdx.x % a.M;
     const int b = unit / a.n_doppler, d = unit % a.n_doppler;
-    // Let the dependent grid (correlate_*) start its prologue as soon as every CTA of this grid has started; it still
-    // waits (griddepcontrol.wait) for this whole grid to finish before it reads the spectra.
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // (No early griddepcontrol.launch_dependents here: measured on B200 it let the FIRST dependent launch of a fresh
+    // engine read the spectra before they were written; the implicit trigger at grid completion keeps the launch-latency
+    // overlap -- 30.4 -> 27.9 us for a one-block search -- and is correct.)
     const double f = a.doppler[d];
     if (isnan(f)) return;  // slot switched off by the on-device search planner
     const float2* __restrict__ src = a.iq + static_cast<size_t>(b) * a.block_stride + static_cast<size_t>(i) * a.N;
@@ -746,7 +748,8 @@ static void launch_dependent(K kernel, const CorrelateArgs& a, int grid, int blo
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    static const bool pdl = !(getenv("GB200_PDL") && atoi(getenv("GB200_PDL")) == 0);
+    cfg.numAttrs = pdl ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kernel, a);
 }
 
