@@ -52,6 +52,8 @@ SYMBOLS = {
     "gb200_tracker_get_state": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                           C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "gb200_tracker_set_state": (C.c_int, [_P, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int32]),
+    "gb200_tracker_integrate_bits": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_int32, _P]),
+    "gb200_tracker_bit_state": (C.c_int, [_P, C.c_int, _P]),
     "gb200_set_fused": (C.c_int, [_P, C.c_int]),
     "gb200_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "gb200_enable_kernel_timing": (C.c_int, [_P, C.c_int]),
@@ -265,6 +267,34 @@ class Tracker:
         self._engine._check(self._lib.gb200_tracker_process_device(self._h, n_ms, _ptr(start_times), _P(out_device_ptr)),
                             "gb200_tracker_process_device")
 
+    def integrate_bits(self, n_ms: int, start_times, end_times, records_device_ptr: int | None = None) -> list:
+        """navigation_bit_intergrator.py:278-288 for every channel over records in device memory (default: the ones the
+        last `process` call left there).  Returns one BIT_DTYPE array per channel."""
+        t0 = np.ascontiguousarray(start_times, dtype=np.float64)
+        t1 = np.ascontiguousarray(end_times, dtype=np.float64)
+        if t0.shape != (n_ms,) or t1.shape != (n_ms,):
+            raise ValueError("start_times / end_times must hold one timestamp per millisecond")
+        cap = n_ms // 20 + 8  # whole bits in the call + the backlog a first phase decision releases (<= 81 symbols)
+        ev = np.empty((self.n_channels, cap), dtype=BIT_DTYPE)
+        cnt = np.empty(self.n_channels, dtype=np.int32)
+        self._engine._check(
+            self._lib.gb200_tracker_integrate_bits(self._h, n_ms, _ptr(t0), _ptr(t1),
+                                                   None if records_device_ptr is None else _P(records_device_ptr),
+                                                   _ptr(ev), cap, _ptr(cnt)), "gb200_tracker_integrate_bits")
+        if (cnt > cap).any():
+            raise RuntimeError("bit event buffer too small")  # cannot happen: see `cap`
+        return [ev[c, : cnt[c]].copy() for c in range(self.n_channels)]
+
+    def bit_state(self, channel: int) -> dict:
+        out = np.zeros(8, dtype=np.int64)
+        self._engine._check(self._lib.gb200_tracker_bit_state(self._h, channel, _ptr(out)), "gb200_tracker_bit_state")
+        keys = ("emitted_bit_count", "failed_bit_count", "processed_pseudosymbol_count", "slide", "determined_bit_phase",
+                "previous_bit_phase_decision", "pseudosymbol_cursor_within_queue", "stopped")
+        d = dict(zip(keys, (int(v) for v in out)))
+        for k in ("determined_bit_phase", "previous_bit_phase_decision"):
+            d[k] = None if d[k] < 0 else d[k]
+        return d
+
     def get_state(self, channel: int) -> dict:
         d, c, a = C.c_double(), C.c_double(), C.c_double()
         p, lost = C.c_int32(), C.c_int32()
@@ -275,6 +305,12 @@ class Tracker:
     def set_state(self, channel: int, doppler: float, carrier_phase: float, phase_acc: float, code_phase: int) -> None:
         self._engine._check(self._lib.gb200_tracker_set_state(self._h, channel, float(doppler), float(carrier_phase),
                                                               float(phase_acc), int(code_phase)), "gb200_tracker_set_state")
+
+
+BIT_DTYPE = np.dtype([  # gb200_bit_event
+    ("receiver_timestamp", "<f8"), ("trailing_edge_receiver_timestamp", "<f8"), ("ms_index", "<i4"), ("bit_value", "<i4"),
+    ("slide", "<i4"), ("pad_", "<i4")])
+assert BIT_DTYPE.itemsize == 32
 
 
 def strength_from_records(rec: np.ndarray, n: int) -> np.ndarray:

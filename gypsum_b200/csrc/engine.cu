@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/gypsum_b200.h"
+#include "bits_core.cuh"
 #include "kernels.cuh"
 
 using namespace gb;
@@ -156,8 +157,17 @@ struct gb200_tracker {
     PinnedBuf<TrackMsRecord> h_out;
     PinnedBuf<double> h_times;
     PinnedBuf<float> h_prof;
+    int last_n_ms = 0;  // records of the last gb200_tracker_process call still in d_out
+    DevBuf<BitState> bit_states;
+    DevBuf<BitEvent> d_events;
+    DevBuf<int> d_counts;
+    DevBuf<double> d_bit_times;
+    PinnedBuf<BitEvent> h_events;
+    PinnedBuf<int> h_counts;
+    PinnedBuf<double> h_bit_times;
 };
 static_assert(sizeof(gb200_track_record) == sizeof(TrackMsRecord), "ABI track record and device record must match");
+static_assert(sizeof(gb200_bit_event) == sizeof(BitEvent), "ABI bit event and device event must match");
 
 #define GB_FAIL(e, code, ...)                        \
     do {                                             \
@@ -999,6 +1009,13 @@ int gb200_tracker_destroy(gb200_tracker* t) {
     t->h_out.release();
     t->h_times.release();
     t->h_prof.release();
+    t->bit_states.release();
+    t->d_events.release();
+    t->d_counts.release();
+    t->d_bit_times.release();
+    t->h_events.release();
+    t->h_counts.release();
+    t->h_bit_times.release();
     delete t;
     return GB200_OK;
 }
@@ -1059,8 +1076,10 @@ int gb200_tracker_process(gb200_tracker* t, int n_ms, const double* start_times,
         GB_CUDA(e, t->d_prof.ensure(np));
         GB_CUDA(e, t->h_prof.ensure(np));
     }
+    t->last_n_ms = 0;
     int rc = tracker_launch(t, n_ms, start_times, t->d_out.p, np ? t->d_prof.p : nullptr);
     if (rc) return rc;
+    t->last_n_ms = n_ms;
     GB_CUDA(e, cudaMemcpyAsync(t->h_out.p, t->d_out.p, n * sizeof(TrackMsRecord), cudaMemcpyDeviceToHost, e->stream));
     if (np) GB_CUDA(e, cudaMemcpyAsync(t->h_prof.p, t->d_prof.p, np * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     GB_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -1101,6 +1120,80 @@ int gb200_tracker_set_state(gb200_tracker* t, int channel, double doppler_hz, do
     st.phase_acc = phase_acc;
     st.code_phase = code_phase;
     GB_CUDA(e, cudaMemcpy(t->states.p + channel, &st, head, cudaMemcpyHostToDevice));
+    return GB200_OK;
+}
+
+int gb200_tracker_integrate_bits(gb200_tracker* t, int n_ms, const double* start_times, const double* end_times,
+                                 const void* records_device, gb200_bit_event* events_host, int32_t max_events,
+                                 int32_t* counts_host) {
+    if (!t) return GB200_EINVAL;
+    gb200_engine* e = t->e;
+    if (n_ms < 1 || !start_times || !end_times) GB_FAIL(e, GB200_EINVAL, "need at least one millisecond and its timestamps");
+    if (!events_host || !counts_host || max_events < 1) GB_FAIL(e, GB200_EINVAL, "null / empty event buffer");
+    if (!records_device && t->last_n_ms != n_ms)
+        GB_FAIL(e, GB200_ESTATE, "no records of %d ms on the device (last gb200_tracker_process call held %d)", n_ms, t->last_n_ms);
+    GB_CUDA(e, cudaSetDevice(e->device));
+    GB_CUDA(e, cudaStreamSynchronize(e->stream));  // pinned staging may still be in flight
+    const int nc = t->n_channels;
+    if (!t->bit_states.p) {
+        std::vector<BitState> init(nc);
+        for (int c = 0; c < nc; ++c) {
+            memset(&init[c], 0, sizeof(BitState));
+            bit_state_init(init[c]);
+        }
+        GB_CUDA(e, t->bit_states.ensure(nc));
+        GB_CUDA(e, cudaMemcpy(t->bit_states.p, init.data(), sizeof(BitState) * nc, cudaMemcpyHostToDevice));
+    }
+    const size_t ne = static_cast<size_t>(nc) * max_events;
+    GB_CUDA(e, t->d_events.ensure(ne));
+    GB_CUDA(e, t->h_events.ensure(ne));
+    GB_CUDA(e, t->d_counts.ensure(nc));
+    GB_CUDA(e, t->h_counts.ensure(nc));
+    GB_CUDA(e, t->d_bit_times.ensure(2 * static_cast<size_t>(n_ms)));
+    GB_CUDA(e, t->h_bit_times.ensure(2 * static_cast<size_t>(n_ms)));
+    memcpy(t->h_bit_times.p, start_times, sizeof(double) * n_ms);
+    memcpy(t->h_bit_times.p + n_ms, end_times, sizeof(double) * n_ms);
+    GB_CUDA(e, cudaMemcpyAsync(t->d_bit_times.p, t->h_bit_times.p, 2 * sizeof(double) * n_ms, cudaMemcpyHostToDevice, e->stream));
+    BitArgs a{};
+    a.records = records_device ? static_cast<const TrackMsRecord*>(records_device) : t->d_out.p;
+    a.start_times = t->d_bit_times.p;
+    a.end_times = t->d_bit_times.p + n_ms;
+    a.states = t->bit_states.p;
+    a.events = t->d_events.p;
+    a.counts = t->d_counts.p;
+    a.n_ms = n_ms;
+    a.n_channels = nc;
+    a.max_events = max_events;
+    GB_CUDA(e, launch_integrate_bits(a, e->stream));
+    e->launches++;
+    GB_CUDA(e, cudaMemcpyAsync(t->h_events.p, t->d_events.p, ne * sizeof(BitEvent), cudaMemcpyDeviceToHost, e->stream));
+    GB_CUDA(e, cudaMemcpyAsync(t->h_counts.p, t->d_counts.p, nc * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    GB_CUDA(e, cudaStreamSynchronize(e->stream));
+    memcpy(events_host, t->h_events.p, ne * sizeof(BitEvent));
+    memcpy(counts_host, t->h_counts.p, nc * sizeof(int));
+    return GB200_OK;
+}
+
+int gb200_tracker_bit_state(gb200_tracker* t, int channel, int64_t out[8]) {
+    if (!t) return GB200_EINVAL;
+    gb200_engine* e = t->e;
+    if (channel < 0 || channel >= t->n_channels || !out) GB_FAIL(e, GB200_EINVAL, "channel %d out of range", channel);
+    BitState st;
+    memset(&st, 0, sizeof(st));
+    bit_state_init(st);
+    if (t->bit_states.p) {
+        GB_CUDA(e, cudaSetDevice(e->device));
+        GB_CUDA(e, cudaStreamSynchronize(e->stream));
+        GB_CUDA(e, cudaMemcpy(&st, t->bit_states.p + channel, sizeof(BitHead), cudaMemcpyDeviceToHost));
+    }
+    out[0] = st.h.emitted;
+    out[1] = st.h.failed;
+    out[2] = st.h.processed;
+    out[3] = st.h.slide;
+    out[4] = st.h.determined;
+    out[5] = st.h.prev_decision;
+    out[6] = st.h.cursor;
+    out[7] = st.h.stopped;
     return GB200_OK;
 }
 

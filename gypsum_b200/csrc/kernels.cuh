@@ -80,6 +80,19 @@ struct TrackArgs {
     int N, s, n_ms, n_channels;
 };
 
+// integrate_bits: one warp per tracking channel (bits.cu, bits_core.cuh).
+struct BitState;
+struct BitEvent;
+struct BitArgs {
+    const TrackMsRecord* records;  // [n_channels][n_ms] as written by k_track_channels
+    const double* start_times;     // [n_ms] chunk start / end timestamps
+    const double* end_times;
+    BitState* states;              // [n_channels]
+    BitEvent* events;              // [n_channels][max_events]
+    int* counts;                   // [n_channels] events produced (may exceed max_events: truncated)
+    int n_ms, n_channels, max_events;
+};
+
 // acquire_fused: one CTA per (PRN, Doppler) cell, the whole pipeline in one kernel (fused.cu).
 struct FusedArgs {
     const float2* iq;       // [M*N] one block
@@ -100,6 +113,7 @@ cudaError_t launch_acquire_fused(const FusedArgs& a, int s, int kind, cudaStream
 size_t track_smem_bytes(int N, int s);
 cudaError_t configure_track_kernel();
 cudaError_t launch_track_channels(const TrackArgs& a, cudaStream_t st);
+cudaError_t launch_integrate_bits(const BitArgs& a, cudaStream_t st);
 size_t spectra_smem_bytes(int s);
 bool spectra_supports(int s);
 size_t correlate_smem_bytes(int np);

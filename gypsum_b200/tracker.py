@@ -218,3 +218,9 @@ class TrackerBank:
         self.engine.upload_iq(x[: n_ms * self.samples_per_ms])
         self._ent["last_chunk"] = None
         return self.native.process(n_ms, start_times, want_profiles)
+
+    def integrate_bits(self, start_times, end_times) -> list:
+        """Navigation bits of every channel from the records the last `process` call left on the device
+        (navigation_bit_intergrator.py:278-288; one integrator per channel, persistent across calls).  Returns one
+        _native.BIT_DTYPE array per channel: timestamps of the bit's edges, value 1 / 0 / -1 (unknown)."""
+        return self.native.integrate_bits(len(start_times), start_times, end_times)

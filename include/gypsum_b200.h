@@ -147,6 +147,31 @@ int gb200_tracker_get_state(gb200_tracker* t, int channel, double* doppler_hz, d
 int gb200_tracker_set_state(gb200_tracker* t, int channel, double doppler_hz, double carrier_phase, double phase_acc,
                             int32_t code_phase);
 
+/* Pseudosymbol -> navigation bit integration (gypsum/navigation_bit_intergrator.py), the consumer of the tracker's
+ * +-1 stream (satellite_signal_processing_pipeline.py:77-79).  One EmitNavigationBitEvent (:29-39), 32 bytes. */
+typedef struct gb200_bit_event {
+    double receiver_timestamp;               /* start_of_pseudosymbol of the bit's first symbol      (:188) */
+    double trailing_edge_receiver_timestamp; /* end_of_pseudosymbol of its last symbol               (:189) */
+    int32_t ms_index;   /* millisecond (within this call) whose symbol completed the bit                    */
+    int32_t bit_value;  /* 1 = BitValue.ONE, 0 = BitValue.ZERO, -1 = BitValue.UNKNOWN                (:149-161) */
+    int32_t slide;      /* NavigationBitIntegrator.slide when the bit was emitted                           */
+    int32_t pad_;
+} gb200_bit_event;
+
+/* NavigationBitIntegrator.process_pseudosymbol (:278-288) for every channel over n_ms millisecond records that are
+ * in device memory: records_device ([channel][n_ms] gb200_track_record), or NULL for the records the last
+ * gb200_tracker_process call of this tracker left on the device (same n_ms).  start_times / end_times: the chunk
+ * timestamps (antenna_sample_provider.py:88-91); receiver_timestamp of :278 is the chunk start.  Each channel keeps
+ * one integrator (bit phase, queue, health history) across calls; a channel whose record says `lost` stops there.
+ * events_host: [channel][max_events]; counts_host: [channel] events produced (> max_events means truncated). */
+int gb200_tracker_integrate_bits(gb200_tracker* t, int n_ms, const double* start_times, const double* end_times,
+                                 const void* records_device, gb200_bit_event* events_host, int32_t max_events,
+                                 int32_t* counts_host);
+/* history of one channel's integrator: out[0..7] = emitted_bit_count, failed_bit_count, processed_pseudosymbol_count,
+ * slide, determined_bit_phase (-1 = None), previous_bit_phase_decision (-1 = None), pseudosymbol_cursor_within_queue,
+ * stopped. */
+int gb200_tracker_bit_state(gb200_tracker* t, int channel, int64_t out[8]);
+
 /* Kernel selection for gb200_acquire_cells.  Two implementations of the same arithmetic exist:
  *   0  doppler_spectra + correlate_cells: the PRN-independent half of the pipeline (wipe-off, forward transform) is
  *      computed once per distinct Doppler bin and shared by every PRN -- the grid shape (gb200_acquire_grid always

@@ -237,3 +237,30 @@ extern "C" void emu_ifft2048_pruned(const float2* y_even, const float2* y_odd, f
         for (int k2 = 0; k2 < 32; ++k2) out[lane + 32 * k2] = make_float2(re[k2], im[k2]);
     }
 }
+
+// ---- navigation bit integration (bits_core.cuh) on the host ----
+#include "../../gypsum_b200/csrc/bits_core.cuh"
+extern "C" {
+int emu_bit_state_size() { return (int)sizeof(BitState); }
+void emu_bit_init(BitState* st) {
+    memset(st, 0, sizeof(BitState));
+    bit_state_init(*st);
+}
+// n symbols of one channel; returns the number of events (may exceed max_events)
+int emu_bit_run(BitState* st, int n, const int* symbols, const double* recv_ts, const double* start, const double* end,
+                BitEvent* out, int max_events) {
+    int n_out = 0;
+    for (int k = 0; k < n; ++k) bit_step(st->h, *st, symbols[k], recv_ts[k], start[k], end[k], k, out, max_events, n_out);
+    return n_out;
+}
+void emu_bit_summary(const BitState* st, long long* out /*[8]*/) {
+    out[0] = st->h.emitted;
+    out[1] = st->h.failed;
+    out[2] = st->h.processed;
+    out[3] = st->h.slide;
+    out[4] = st->h.determined;
+    out[5] = st->h.prev_decision;
+    out[6] = st->h.cursor;
+    out[7] = st->h.overflow;
+}
+}

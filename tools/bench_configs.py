@@ -151,12 +151,22 @@ def tracker_case(n_ch, n_ms):
     trk.process_device(n_ms, times, out.data_ptr())
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    # navigation bits from the records where the tracking kernel left them
+    ends = times + n / fs
+    trk.integrate_bits(min(n_ms, 1000), times[:1000], ends[:1000], out.data_ptr())  # warm-up (allocations); state is reset below
+    trk.close()
+    trk = _native.Tracker(eng, [c[0] - 1 for c in chans], [c[1] for c in chans], [0.0] * n_ch, [c[3] for c in chans])
+    t0 = time.perf_counter()
+    bits = trk.integrate_bits(n_ms, times, ends, out.data_ptr())
+    dt_bits = time.perf_counter() - t0
     rec = out.cpu().numpy().view(_native.TRACK_DTYPE).reshape(n_ch, n_ms)
     print(json.dumps({"workload": f"config 4: {n_ch}-channel E/P/L tracking, {n_ms / 1000:.0f} s of IQ @ 2.046 Msps",
                       "seconds": dt, "channel_ms_per_s": n_ch * n_ms / dt, "us_per_ms_per_channel_stream": dt / n_ms * 1e6,
                       "realtime_factor": (n_ms / 1000) / dt, "Msamples_per_s_stream": n_ms * n / dt / 1e6,
                       "locked_fraction_last_second": float(rec["locked"][:, -1000:].mean()),
-                      "lost_channels": int((rec["lost"] > 0).any(axis=1).sum())}), flush=True)
+                      "lost_channels": int((rec["lost"] > 0).any(axis=1).sum()),
+                      "bit_integration_seconds": dt_bits, "bits_emitted": int(sum(len(b) for b in bits)),
+                      "bits_unknown": int(sum((b["bit_value"] < 0).sum() for b in bits))}), flush=True)
     trk.close()
     eng.close()
 
