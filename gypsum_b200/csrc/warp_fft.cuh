@@ -256,11 +256,11 @@ GB_HD GB_INLINE void thread_peak16(const float (&v)[16], int lane, int h, int s,
     float sm = v[0];
 #pragma unroll
     for (int jj = 1; jj < 15; ++jj) {
-        m = m > v[jj] ? m : v[jj];
+        m = fmaxf(m, v[jj]);  // magnitudes: no NaN ordering to preserve; one FMNMX(3) instead of FSETP + FSEL
         sm += v[jj];
     }
     const float v15 = last_invalid ? -1.0f : v[15];
-    m = m > v15 ? m : v15;
+    m = fmaxf(m, v15);
     sm += last_invalid ? 0.0f : v[15];
     int first = 15, c = 0;
     {
