@@ -467,7 +467,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_correlate_w2048(const CorrelateA
             mbar_wait(mbar, parity);
             parity ^= 1;
             cur_prn = prn;
-            __nanosleep(warp * 150);  // de-phase the warps after the CTA-wide barrier
+            // de-phase the warps after the CTA-wide barrier (they would otherwise hit their memory phases together)
+            __nanosleep((warp >> 2) * a.stag_a + (warp & 3) * a.stag_b);
         }
 
         if (active) {
@@ -766,7 +767,12 @@ static void correlate_dispatch(const CorrelateArgs& a, int grid, cudaStream_t st
     }
 }
 // One-warp-per-transform build: nw = 10 warps needs M == 1 (the caller guarantees it), nw = 8 takes any M.
-cudaError_t launch_correlate_w2048(const CorrelateArgs& a, int nw, int grid, cudaStream_t st) {
+cudaError_t launch_correlate_w2048(const CorrelateArgs& a0, int nw, int grid, cudaStream_t st) {
+    static const int stag_a = [] { const char* v = getenv("GB200_STAGGER_A"); return v ? atoi(v) : 600; }();
+    static const int stag_b = [] { const char* v = getenv("GB200_STAGGER_B"); return v ? atoi(v) : 150; }();
+    CorrelateArgs a = a0;
+    a.stag_a = stag_a;
+    a.stag_b = stag_b;
     if (nw == 12) launch_dependent(k_correlate_w2048<12, true>, a, grid, 384, correlate_w2048_smem_bytes(12), st);
     else if (nw == 10) launch_dependent(k_correlate_w2048<10, true>, a, grid, 320, correlate_w2048_smem_bytes(10), st);
     else launch_dependent(k_correlate_w2048<8, false>, a, grid, 256, correlate_w2048_smem_bytes(8), st);

@@ -41,6 +41,7 @@ struct CorrelateArgs {
     const int* cell_u;      // spectrum unit of each sorted cell
     const int* cell_out;    // where its record goes
     const int* cell_probe;  // coherent probe index or -1 (both modes, indexed by output slot; may be null)
+    int stag_a, stag_b;       // k_correlate_w2048 start stagger in ns: (warp / 4) * stag_a + (warp % 4) * stag_b
     const double* cell_gate;  // optional, indexed by output slot: NaN = this cell is switched off (device-planned lists)
 };
 
