@@ -52,6 +52,10 @@ SYMBOLS = {
     "gb200_tracker_get_state": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                           C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "gb200_tracker_set_state": (C.c_int, [_P, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int32]),
+    "gb200_grid_stream_create": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "gb200_grid_stream_submit": (C.c_int, [_P, _P, _P]),
+    "gb200_grid_stream_collect": (C.c_int, [_P]),
+    "gb200_grid_stream_destroy": (C.c_int, [_P]),
     "gb200_tracker_integrate_bits": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_int32, _P]),
     "gb200_tracker_bit_state": (C.c_int, [_P, C.c_int, _P]),
     "gb200_set_fused": (C.c_int, [_P, C.c_int]),
@@ -221,6 +225,63 @@ class Engine:
             "gb200_correlation_profile",
         )
         return out.view(np.complex64) if kind == COHERENT else out
+
+
+class GridStream:
+    """Pipelined stream of equally shaped grid batches (gb200_grid_stream_*): `submit` enqueues copy-in, the grid and
+    copy-out of one batch, `collect` waits for the oldest batch in flight and returns its record array.  With depth >= 2
+    the transfers of neighbouring batches run under the kernels of the current one."""
+
+    def __init__(self, engine: Engine, n_blocks: int, ms_per_block: int, prn_idx, doppler_hz, kind: int = NON_COHERENT,
+                 depth: int = 2):
+        self._engine = engine
+        self._lib = engine._lib
+        prn = np.ascontiguousarray(prn_idx, dtype=np.int32)
+        dop = np.ascontiguousarray(doppler_hz, dtype=np.float64)
+        self.shape = (n_blocks, prn.size, dop.size)
+        self.samples_per_batch = n_blocks * ms_per_block * engine.samples_per_ms
+        self.depth = depth
+        self._pending: list = []  # (iq keep-alive, out array) per batch in flight
+        self._h = _P()
+        engine._check(self._lib.gb200_grid_stream_create(engine._h, n_blocks, ms_per_block, _ptr(prn), prn.size, _ptr(dop),
+                                                         dop.size, kind, depth, C.byref(self._h)), "gb200_grid_stream_create")
+
+    @property
+    def in_flight(self) -> int:
+        return len(self._pending)
+
+    def submit(self, iq, out: np.ndarray | None = None) -> None:
+        """iq: complex64 array of samples_per_batch samples, or an int host address of such a buffer.  out: optional
+        RECORD_DTYPE array [n_blocks, n_prn, n_doppler] (pinned memory = direct DMA)."""
+        if isinstance(iq, (int, np.integer)):
+            keep, ptr = None, _P(int(iq))
+        else:
+            keep = np.ascontiguousarray(iq, dtype=np.complex64)
+            if keep.size != self.samples_per_batch:
+                raise ValueError(f"a batch is {self.samples_per_batch} samples, got {keep.size}")
+            ptr = _ptr(keep)
+        if out is None:
+            out = np.empty(self.shape, dtype=RECORD_DTYPE)
+        elif out.dtype != RECORD_DTYPE or out.shape != self.shape or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("out must be a C-contiguous RECORD_DTYPE array of shape [n_blocks, n_prn, n_doppler]")
+        self._engine._check(self._lib.gb200_grid_stream_submit(self._h, ptr, _ptr(out)), "gb200_grid_stream_submit")
+        self._pending.append((keep, out))
+
+    def collect(self) -> np.ndarray:
+        self._engine._check(self._lib.gb200_grid_stream_collect(self._h), "gb200_grid_stream_collect")
+        return self._pending.pop(0)[1]
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and getattr(self._engine, "_h", None):
+            self._lib.gb200_grid_stream_destroy(self._h)
+        self._h = None
+        self._pending = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Tracker:

@@ -166,6 +166,26 @@ struct gb200_tracker {
     PinnedBuf<int> h_counts;
     PinnedBuf<double> h_bit_times;
 };
+// A pipelined stream of grid batches: slot k's host->device copy, compute and device->host copy run on three streams.
+struct gb200_grid_stream {
+    gb200_engine* e = nullptr;
+    int n_blocks = 0, M = 0, P = 0, D = 0, kind = 0, depth = 0;
+    std::vector<int32_t> prn;
+    std::vector<double> dop;
+    struct Slot {
+        DevBuf<float2> iq;
+        DevBuf<CellRecord> rec;
+        PinnedBuf<float2> h_iq;       // staging, only when the caller's IQ is pageable
+        PinnedBuf<CellRecord> h_rec;  // staging, only when the caller's record buffer is pageable
+        gb200_cell_record* out = nullptr;  // where this batch's records go
+        bool staged_out = false;
+        cudaEvent_t h2d = nullptr, done = nullptr, d2h = nullptr;
+    };
+    std::vector<Slot> slots;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    long long head = 0, tail = 0;  // batches submitted / collected
+};
+
 static_assert(sizeof(gb200_track_record) == sizeof(TrackMsRecord), "ABI track record and device record must match");
 static_assert(sizeof(gb200_bit_event) == sizeof(BitEvent), "ABI bit event and device event must match");
 
@@ -1194,6 +1214,119 @@ int gb200_tracker_bit_state(gb200_tracker* t, int channel, int64_t out[8]) {
     out[5] = st.h.prev_decision;
     out[6] = st.h.cursor;
     out[7] = st.h.stopped;
+    return GB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// pipelined grid batches
+// ---------------------------------------------------------------------------------------------------------
+int gb200_grid_stream_destroy(gb200_grid_stream* g) {
+    if (!g) return GB200_OK;
+    cudaSetDevice(g->e->device);
+    cudaStreamSynchronize(g->e->stream);
+    if (g->s_in) cudaStreamSynchronize(g->s_in);
+    if (g->s_out) cudaStreamSynchronize(g->s_out);
+    for (auto& sl : g->slots) {
+        sl.iq.release();
+        sl.rec.release();
+        sl.h_iq.release();
+        sl.h_rec.release();
+        if (sl.h2d) cudaEventDestroy(sl.h2d);
+        if (sl.done) cudaEventDestroy(sl.done);
+        if (sl.d2h) cudaEventDestroy(sl.d2h);
+    }
+    if (g->s_in) cudaStreamDestroy(g->s_in);
+    if (g->s_out) cudaStreamDestroy(g->s_out);
+    delete g;
+    return GB200_OK;
+}
+
+int gb200_grid_stream_create(gb200_engine* e, int n_blocks, int M, const int32_t* prn_idx, int P, const double* dop, int D,
+                             int kind, int depth, gb200_grid_stream** out) {
+    if (!e) return GB200_EINVAL;
+    if (!out) GB_FAIL(e, GB200_EINVAL, "null output");
+    *out = nullptr;
+    if (n_blocks < 1 || P < 1 || D < 1 || !prn_idx || !dop) GB_FAIL(e, GB200_EINVAL, "empty grid");
+    if (depth < 1 || depth > 8) GB_FAIL(e, GB200_EINVAL, "depth must be 1..8");
+    int rc = check_common(e, M, kind);
+    if (rc) return rc;
+    for (int i = 0; i < P; ++i)
+        if (prn_idx[i] < 0 || prn_idx[i] >= e->n_prn) GB_FAIL(e, GB200_EINVAL, "prn index %d out of range", prn_idx[i]);
+    GB_CUDA(e, cudaSetDevice(e->device));
+    gb200_grid_stream* g = new gb200_grid_stream;
+    g->e = e;
+    g->n_blocks = n_blocks;
+    g->M = M;
+    g->P = P;
+    g->D = D;
+    g->kind = kind;
+    g->depth = depth;
+    g->prn.assign(prn_idx, prn_idx + P);
+    g->dop.assign(dop, dop + D);
+    g->slots.resize(depth);
+    const size_t n_iq = static_cast<size_t>(n_blocks) * M * e->N, n_rec = static_cast<size_t>(n_blocks) * P * D;
+    cudaError_t ce = cudaStreamCreateWithFlags(&g->s_in, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&g->s_out, cudaStreamNonBlocking);
+    for (auto& sl : g->slots) {
+        if (ce == cudaSuccess) ce = sl.iq.ensure(n_iq);
+        if (ce == cudaSuccess) ce = sl.rec.ensure(n_rec);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&sl.h2d, cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&sl.d2h, cudaEventDisableTiming);
+    }
+    if (ce != cudaSuccess) {
+        gb200_grid_stream_destroy(g);
+        cudaGetLastError();
+        GB_FAIL(e, GB200_ECUDA, "grid stream allocation failed: %s", cudaGetErrorString(ce));
+    }
+    *out = g;
+    return GB200_OK;
+}
+
+int gb200_grid_stream_submit(gb200_grid_stream* g, const float* iq_host, gb200_cell_record* out_host) {
+    if (!g) return GB200_EINVAL;
+    gb200_engine* e = g->e;
+    if (!iq_host || !out_host) GB_FAIL(e, GB200_EINVAL, "null buffer");
+    if (g->head - g->tail >= g->depth) GB_FAIL(e, GB200_ESTATE, "%d batches in flight: collect one first", g->depth);
+    GB_CUDA(e, cudaSetDevice(e->device));
+    auto& sl = g->slots[g->head % g->depth];
+    const size_t n_iq = static_cast<size_t>(g->n_blocks) * g->M * e->N, n_rec = static_cast<size_t>(g->n_blocks) * g->P * g->D;
+    // the slot's previous batch was collected, so its device buffers and staging are free
+    const void* src = iq_host;
+    if (!is_pinned_host(iq_host)) {
+        GB_CUDA(e, sl.h_iq.ensure(n_iq));
+        memcpy(sl.h_iq.p, iq_host, n_iq * sizeof(float2));
+        src = sl.h_iq.p;
+    }
+    sl.out = out_host;
+    sl.staged_out = !is_pinned_host(out_host);
+    if (sl.staged_out) GB_CUDA(e, sl.h_rec.ensure(n_rec));
+    GB_CUDA(e, cudaMemcpyAsync(sl.iq.p, src, n_iq * sizeof(float2), cudaMemcpyHostToDevice, g->s_in));
+    GB_CUDA(e, cudaEventRecord(sl.h2d, g->s_in));
+    GB_CUDA(e, cudaStreamWaitEvent(e->stream, sl.h2d, 0));
+    e->iq = sl.iq.p;
+    e->iq_samples = static_cast<int64_t>(n_iq);
+    int rc = run_grid(e, g->n_blocks, g->M, g->prn.data(), g->P, g->dop.data(), g->D, g->kind, sl.rec.p);
+    if (rc) return rc;
+    GB_CUDA(e, cudaEventRecord(sl.done, e->stream));
+    GB_CUDA(e, cudaStreamWaitEvent(g->s_out, sl.done, 0));
+    GB_CUDA(e, cudaMemcpyAsync(sl.staged_out ? reinterpret_cast<gb200_cell_record*>(sl.h_rec.p) : out_host, sl.rec.p,
+                               n_rec * sizeof(CellRecord), cudaMemcpyDeviceToHost, g->s_out));
+    GB_CUDA(e, cudaEventRecord(sl.d2h, g->s_out));
+    g->head++;
+    return GB200_OK;
+}
+
+int gb200_grid_stream_collect(gb200_grid_stream* g) {
+    if (!g) return GB200_EINVAL;
+    gb200_engine* e = g->e;
+    if (g->head == g->tail) GB_FAIL(e, GB200_ESTATE, "no batch in flight");
+    GB_CUDA(e, cudaSetDevice(e->device));
+    auto& sl = g->slots[g->tail % g->depth];
+    GB_CUDA(e, cudaEventSynchronize(sl.d2h));
+    if (sl.staged_out)
+        memcpy(sl.out, sl.h_rec.p, static_cast<size_t>(g->n_blocks) * g->P * g->D * sizeof(CellRecord));
+    g->tail++;
     return GB200_OK;
 }
 

@@ -147,6 +147,20 @@ int gb200_tracker_get_state(gb200_tracker* t, int channel, double* doppler_hz, d
 int gb200_tracker_set_state(gb200_tracker* t, int channel, double doppler_hz, double carrier_phase, double phase_acc,
                             int32_t code_phase);
 
+/* A pipelined stream of equally shaped grid batches -- the receiver's steady state (receiver.py:85-146 hands over one
+ * block after another): `submit` copies a batch of n_blocks*M*N complex64 samples from host memory, runs the grid of
+ * gb200_acquire_grid on it and sends the n_blocks*P*D records to out_host; `collect` waits for the OLDEST batch in
+ * flight.  Up to `depth` batches are in flight: the host->device copy of batch k+1 and the device->host copy of batch
+ * k-1 run on their own streams under the kernels of batch k.  iq_host / out_host are DMA'd directly when they are
+ * pinned, staged otherwise; both must stay valid until the batch is collected.  While a stream exists it owns the
+ * engine's IQ binding (gb200_upload_iq / gb200_bind_iq_device must be called again before other acquire calls). */
+typedef struct gb200_grid_stream gb200_grid_stream;
+int gb200_grid_stream_create(gb200_engine* e, int n_blocks, int n_ms, const int32_t* prn_idx, int n_prn,
+                             const double* doppler_hz, int n_doppler, int kind, int depth, gb200_grid_stream** out);
+int gb200_grid_stream_submit(gb200_grid_stream* g, const float* iq_host, gb200_cell_record* out_host);
+int gb200_grid_stream_collect(gb200_grid_stream* g);
+int gb200_grid_stream_destroy(gb200_grid_stream* g);
+
 /* Pseudosymbol -> navigation bit integration (gypsum/navigation_bit_intergrator.py), the consumer of the tracker's
  * +-1 stream (satellite_signal_processing_pipeline.py:77-79).  One EmitNavigationBitEvent (:29-39), 32 bytes. */
 typedef struct gb200_bit_event {
