@@ -185,7 +185,18 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         import torch.distributed as dist_mod
 
         dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL announces its version on stdout when the communicator comes up; keep stdout to the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     B = args.blocks_per_step
     block_bytes = N * 8

@@ -4,6 +4,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -108,6 +109,7 @@ class Engine:
         self.samples_per_ms = int(samples_per_ms)
         self.device = int(device)
         self.n_prn = 0
+        self._children = weakref.WeakSet()  # trackers / grid streams: they hold device memory tied to this engine
 
     # -- plumbing ------------------------------------------------------------------------------------------
     def _check(self, rc: int, what: str) -> None:
@@ -118,6 +120,8 @@ class Engine:
 
     def close(self) -> None:
         if getattr(self, "_h", None):
+            for child in list(getattr(self, "_children", ())):
+                child.close()  # before the engine goes: their buffers live behind its handle's device
             self._lib.gb200_destroy(self._h)
             self._h = None
 
@@ -245,6 +249,7 @@ class GridStream:
         self._h = _P()
         engine._check(self._lib.gb200_grid_stream_create(engine._h, n_blocks, ms_per_block, _ptr(prn), prn.size, _ptr(dop),
                                                          dop.size, kind, depth, C.byref(self._h)), "gb200_grid_stream_create")
+        engine._children.add(self)
 
     @property
     def in_flight(self) -> int:
@@ -300,6 +305,7 @@ class Tracker:
         self._h = _P()
         engine._check(self._lib.gb200_tracker_create(engine._h, prn.size, _ptr(prn), _ptr(dop), _ptr(cph), _ptr(code),
                                                      C.byref(self._h)), "gb200_tracker_create")
+        engine._children.add(self)
 
     def close(self) -> None:
         if getattr(self, "_h", None) and getattr(self._engine, "_h", None):
