@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(2 * S * 32, (S == 2 ? 3 : 1)) k_acquire_fused(
             }
         } else {
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) acc_re[jj] += gb_sqrt(xr[jj] * xr[jj] + xi[jj] * xi[jj]);  // utils.py:104
+            for (int jj = 0; jj < 16; ++jj) acc_re[jj] += gb_mag(xr[jj], xi[jj]);  // utils.py:104
         }
         // the next millisecond's CTA-wide barriers order the tile reuse
     }
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(2 * S * 32, (S == 2 ? 3 : 1)) k_acquire_fused(
 #pragma unroll
     for (int jj = 0; jj < 16; ++jj) {
         if (KIND == kKindCoherent) {
-            v[jj] = gb_sqrt(acc_re[jj] * acc_re[jj] + acc_im[jj] * acc_im[jj]);
+            v[jj] = gb_mag(acc_re[jj], acc_im[jj]);
             const int q = lane + 32 * (16 * h + jj);
             if (q < kChips && S * q + r == probe) {
                 pr_re = acc_re[jj];

@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
                     if (KIND == kKindCoherent) {
 #pragma unroll
                         for (int jj = 0; jj < 16; ++jj) {
-                            acc[jj] = gb_sqrt(xr[jj] * xr[jj] + xi[jj] * xi[jj]);
+                            acc[jj] = gb_mag(xr[jj], xi[jj]);
                             const int q = lane + 32 * (16 * h + jj);
                             const int n = a.s * q + r;
                             if (n == probe && q < kChips) {
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
                         }
                     } else {
 #pragma unroll
-                        for (int jj = 0; jj < 16; ++jj) acc[jj] += gb_sqrt(xr[jj] * xr[jj] + xi[jj] * xi[jj]);
+                        for (int jj = 0; jj < 16; ++jj) acc[jj] += gb_mag(xr[jj], xi[jj]);
                     }
                     pair_barrier(pair);  // partner has read my tile; the next phase 1 may overwrite it
                 }
@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_correlate_w2048(const CorrelateA
                     w2048_phase2(im, re, lane, tile);
                     __syncwarp();  // the tile may be overwritten by the next transform
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) acc[k] += gb_sqrt(re[k] * re[k] + im[k] * im[k]);
+                    for (int k = 0; k < 32; ++k) acc[k] += gb_mag(re[k], im[k]);
                 }
                 // lags q = lane + 32 k: k < 16 and k >= 16 are the two halves thread_peak16 knows as h = 0 / 1
 #pragma unroll

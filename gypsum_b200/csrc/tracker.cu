@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) k_track_channels(const Track
                 const int q = lane + 32 * (16 * h + jj);
                 if (q < kChips) {
                     const int n = S * q + r;
-                    const float v = gb_sqrt(xr[jj] * xr[jj] + xi[jj] * xi[jj]);
+                    const float v = gb_mag(xr[jj], xi[jj]);
                     int kk = n - pm;
                     kk = kk < 0 ? kk + a.N : kk;
                     if (v > mx || (v == mx && kk < key)) {

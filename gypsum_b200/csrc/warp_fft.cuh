@@ -20,9 +20,18 @@
 
 namespace gb {
 
-GB_HD GB_INLINE float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// Every multiply-add on the data path is an explicit fmaf(): the rounding of a product-sum must not depend on which
+// contraction the compiler happens to pick in a given inlining context -- all kernels (and the host lane emulator) that
+// run the same sequence of operations then agree bit for bit, which the parity tests rely on.
+GB_HD GB_INLINE float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x));
+}
 GB_HD GB_INLINE float2 cmulc(float2 a, float2 b) {  // a * conj(b)
-    return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -(a.x * b.y)));
+}
+// e + o * conj(w), two FMAs per component
+GB_HD GB_INLINE float2 cfmac(float2 e, float2 o, float2 w) {
+    return make_float2(fmaf(o.x, w.x, fmaf(o.y, w.y, e.x)), fmaf(o.y, w.x, fmaf(-o.x, w.y, e.y)));
 }
 
 // Pair-interleaved layout used by every per-thread table and vector (spectra, replica spectra, twiddles, exchange
@@ -61,9 +70,8 @@ GB_HD GB_INLINE void wfft_phase1(float (&re)[32], float (&im)[32], int lane, con
         ld_pair(tw1 + 2 * (kp * 32 + lane), w0, w1);
         const int k1 = 2 * kp;
         if (kp == 0) tile[lane] = make_float2(re[0], im[0]);
-        else tile[k1 * kTStride + lane] = make_float2(re[k1] * w0.x - im[k1] * w0.y, re[k1] * w0.y + im[k1] * w0.x);
-        tile[(k1 + 1) * kTStride + lane] =
-            make_float2(re[k1 + 1] * w1.x - im[k1 + 1] * w1.y, re[k1 + 1] * w1.y + im[k1 + 1] * w1.x);
+        else tile[k1 * kTStride + lane] = cmul(make_float2(re[k1], im[k1]), w0);
+        tile[(k1 + 1) * kTStride + lane] = cmul(make_float2(re[k1 + 1], im[k1 + 1]), w1);
     }
 }
 // Phase 2: thread `lane` owns column k1 = lane: reads u[l][lane], l = 0..31, FFT-32 over l.  Afterwards
@@ -104,11 +112,11 @@ GB_HD GB_INLINE void mul_vec(float (&re)[32], float (&im)[32], int lane, const f
     for (int jp = 0; jp < 16; ++jp) {
         float2 a, b;
         ld_pair(w + 2 * (jp * 32 + lane), a, b);
-        const float r0 = re[2 * jp], i0 = im[2 * jp], r1 = re[2 * jp + 1], i1 = im[2 * jp + 1];
-        re[2 * jp] = r0 * a.x - i0 * a.y;
-        im[2 * jp] = r0 * a.y + i0 * a.x;
-        re[2 * jp + 1] = r1 * b.x - i1 * b.y;
-        im[2 * jp + 1] = r1 * b.y + i1 * b.x;
+        const float2 p0 = cmul(make_float2(re[2 * jp], im[2 * jp]), a), p1 = cmul(make_float2(re[2 * jp + 1], im[2 * jp + 1]), b);
+        re[2 * jp] = p0.x;
+        im[2 * jp] = p0.y;
+        re[2 * jp + 1] = p1.x;
+        im[2 * jp + 1] = p1.y;
     }
 }
 // re/im = a[j] * w[j]: load a pair-interleaved vector and multiply in one pass (half-spectrum x replica spectrum)
@@ -118,10 +126,11 @@ GB_HD GB_INLINE void load_mul_vec(float (&re)[32], float (&im)[32], int lane, co
         float2 a0, a1, w0, w1;
         ld_pair(a + 2 * (jp * 32 + lane), a0, a1);
         ld_pair(w + 2 * (jp * 32 + lane), w0, w1);
-        re[2 * jp] = a0.x * w0.x - a0.y * w0.y;
-        im[2 * jp] = a0.x * w0.y + a0.y * w0.x;
-        re[2 * jp + 1] = a1.x * w1.x - a1.y * w1.y;
-        im[2 * jp + 1] = a1.x * w1.y + a1.y * w1.x;
+        const float2 p0 = cmul(a0, w0), p1 = cmul(a1, w1);
+        re[2 * jp] = p0.x;
+        im[2 * jp] = p0.y;
+        re[2 * jp + 1] = p1.x;
+        im[2 * jp + 1] = p1.y;
     }
 }
 
@@ -137,7 +146,7 @@ GB_HD GB_INLINE float2 wipeoff(float2 x, double cycles) {
     const double a = 6.283185307179586476925 * static_cast<double>(static_cast<float>(fr));
     const float s = static_cast<float>(__builtin_sin(a)), c = static_cast<float>(__builtin_cos(a));
 #endif
-    return make_float2(x.x * c + x.y * s, x.y * c - x.x * s);  // x * (c - j s)
+    return cmulc(x, make_float2(c, s));  // x * (c - j s)
 }
 
 // exp(-j 2 pi frac(f * idx / fs)): the carrier at sample index idx, phase reduced in float64 first.
@@ -202,6 +211,8 @@ GB_HD GB_INLINE float gb_sqrt(float x) {
 #endif
 }
 
+GB_HD GB_INLINE float gb_mag(float re, float im) { return gb_sqrt(fmaf(re, re, im * im)); }  // |re + j im|
+
 // Radix-2 recombination of the two inverse half transforms, out[k] = E[k] + conj(W2048^k) O[k], split so both
 // warps of a pair do the same amount of work: the even-bin warp finishes lags k = lane + 32 jj (jj < 16) from
 // its own E and the partner's raw O; the odd-bin warp finishes k = lane + 32 (16 + jj) from its own O and the
@@ -213,10 +224,12 @@ GB_HD GB_INLINE void combine_even(const float (&re)[32], const float (&im)[32], 
         float2 o0, o1, w0, w1;
         ld_pair(theirs + 2 * (p * 32 + lane), o0, o1);
         ld_pair(tw2 + 2 * (p * 32 + lane), w0, w1);
-        xr[2 * p] = re[2 * p] + (o0.x * w0.x + o0.y * w0.y);
-        xi[2 * p] = im[2 * p] + (o0.y * w0.x - o0.x * w0.y);
-        xr[2 * p + 1] = re[2 * p + 1] + (o1.x * w1.x + o1.y * w1.y);
-        xi[2 * p + 1] = im[2 * p + 1] + (o1.y * w1.x - o1.x * w1.y);
+        const float2 x0 = cfmac(make_float2(re[2 * p], im[2 * p]), o0, w0);
+        const float2 x1 = cfmac(make_float2(re[2 * p + 1], im[2 * p + 1]), o1, w1);
+        xr[2 * p] = x0.x;
+        xi[2 * p] = x0.y;
+        xr[2 * p + 1] = x1.x;
+        xi[2 * p + 1] = x1.y;
     }
 }
 GB_HD GB_INLINE void combine_odd(const float (&re)[32], const float (&im)[32], int lane, const float2* tw2,
@@ -227,10 +240,12 @@ GB_HD GB_INLINE void combine_odd(const float (&re)[32], const float (&im)[32], i
         ld_pair(theirs + 2 * (p * 32 + lane), e0, e1);
         ld_pair(tw2 + 2 * ((8 + p) * 32 + lane), w0, w1);
         const int j = 16 + 2 * p;
-        xr[2 * p] = e0.x + (re[j] * w0.x + im[j] * w0.y);
-        xi[2 * p] = e0.y + (im[j] * w0.x - re[j] * w0.y);
-        xr[2 * p + 1] = e1.x + (re[j + 1] * w1.x + im[j + 1] * w1.y);
-        xi[2 * p + 1] = e1.y + (im[j + 1] * w1.x - re[j + 1] * w1.y);
+        const float2 x0 = cfmac(e0, make_float2(re[j], im[j]), w0);
+        const float2 x1 = cfmac(e1, make_float2(re[j + 1], im[j + 1]), w1);
+        xr[2 * p] = x0.x;
+        xi[2 * p] = x0.y;
+        xr[2 * p + 1] = x1.x;
+        xi[2 * p + 1] = x1.y;
     }
 }
 // What each warp hands to its partner (pair-interleaved, [pidx(jj, lane)]): the even-bin warp its E[k] for the upper
@@ -353,9 +368,9 @@ GB_HD GB_INLINE void w2048_phase1(float (&re)[32], float (&im)[32], int lane, co
         for (int q = 0; q < 2; ++q) {
             const int k1 = 2 * kp + q;
             float2 w = q ? w1 : w0;
-            if (H == 1) w = make_float2(w.x * kW[k1][0] - w.y * kW[k1][1], w.x * kW[k1][1] + w.y * kW[k1][0]);
+            if (H == 1) w = cmul(w, make_float2(kW[k1][0], kW[k1][1]));
             if (k1 == 0 && H == 0) row[0] = make_float2(re[0], im[0]);
-            else row[k1] = make_float2(re[k1] * w.x - im[k1] * w.y, re[k1] * w.y + im[k1] * w.x);
+            else row[k1] = cmul(make_float2(re[k1], im[k1]), w);
         }
     }
 }

@@ -162,9 +162,9 @@ void emu_cell_profile(const float2* iq, int N, int n_ms, double fs, double doppl
                         const int q = lane + 32 * (16 * half + jj);
                         const int n = s * q + r;
                         float& a = acc[((size_t)half * 32 + lane) * 16 + jj];
-                        if (kind == 2) a += gb_sqrt(xr[jj] * xr[jj] + xi[jj] * xi[jj]);
+                        if (kind == 2) a += gb_mag(xr[jj], xi[jj]);
                         else {
-                            a = gb_sqrt(xr[jj] * xr[jj] + xi[jj] * xi[jj]);
+                            a = gb_mag(xr[jj], xi[jj]);
                             if (q < kChips) {
                                 out[2 * n] = xr[jj];
                                 out[2 * n + 1] = xi[jj];

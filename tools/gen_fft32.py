@@ -2,8 +2,13 @@
 separate re[]/im[] register arrays, natural order in and out.
 
 Inverse transforms use the same codelet with the re/im arrays swapped (IDFT(x) = swap(DFT(swap(x)))).
-Twiddle constants are folded (1, -j, (1-j)/sqrt2 ... are special-cased); nvcc contracts the mul+add pairs
-into FFMA.  Run:  python tools/gen_fft32.py
+Twiddle constants are folded (1, -j, (1-j)/sqrt2 ... are special-cased) and every split-radix butterfly with
+non-trivial twiddles is written in the factored ("tangent") form, in which the two twiddle products, their sum /
+difference and the four outputs are 16 multiply-adds instead of 20 operations:
+    w^k z = c1 (z.re - t1 z.im, z.im + t1 z.re),  t1 = tan,  and likewise w^3k z' = c3 (...), so that
+    w^k z +- w^3k z' = c1 (a' +- (c3/c1) b')  and  out = u +- c1 (...)  -- each line one FMA per component.
+The multiply-adds are written as fmaf() so that every kernel and the host emulator round identically.
+Run:  python tools/gen_fft32.py
 """
 import math
 import os
@@ -26,6 +31,12 @@ class Emitter:
 
     def lit(self, v):
         return f"{v:.9e}f"
+
+    def fma(self, const, x, y):
+        """const * x + y as an explicit fused multiply-add: the rounding must not depend on the contraction choices the
+        compiler makes in each inlining context (every kernel and the host emulator have to agree bit for bit)."""
+        self.flops += 1
+        return self.tmp(f"fmaf({self.lit(const)}, {x}, {y})")
 
     # complex values are (re_name, im_name) string pairs
     def add(self, a, b):
@@ -79,14 +90,41 @@ class Emitter:
         out = [None] * n
         q = n // 4
         for k in range(q):
-            a = self.mulw(z[k], k, n)
-            b = self.mulw(zp[k], 3 * k, n)
-            s = self.add(a, b)
-            d = self.mul_neg_j(self.sub(a, b))
-            out[k] = self.add(u[k], s)
-            out[k + 2 * q] = self.sub(u[k], s)
-            out[k + q] = self.add(u[k + q], d)
-            out[k + 3 * q] = self.sub(u[k + q], d)
+            if k == 0:
+                a, b = z[0], zp[0]
+                s = self.add(a, b)
+                d = self.mul_neg_j(self.sub(a, b))
+                out[k] = self.add(u[k], s)
+                out[k + 2 * q] = self.sub(u[k], s)
+                out[k + q] = self.add(u[k + q], d)
+                out[k + 3 * q] = self.sub(u[k + q], d)
+                continue
+            # a = w^k z = c1 * a1, b = w^3k z' = c3 * b1 with a1, b1 two operations each
+            if 8 * k == n:  # w = (1 - j)/sqrt2, w^3 = (-1 - j)/sqrt2: c1 = c3 = 1/sqrt2
+                zr, zi = z[k]
+                pr, pi = zp[k]
+                a1 = (self.tmp(f"{zr} + {zi}"), self.tmp(f"{zi} - {zr}"))
+                b1 = (self.tmp(f"{pi} - {pr}"), self.tmp(f"-{pr} - {pi}"))
+                c1 = math.sqrt(0.5)
+                s1 = self.add(a1, b1)
+                d1 = self.sub(a1, b1)
+            else:
+                th1, th3 = -2.0 * math.pi * k / n, -2.0 * math.pi * 3 * k / n
+                c1, c3 = math.cos(th1), math.cos(th3)
+                t1, t3, rho = math.tan(th1), math.tan(th3), c3 / c1
+                zr, zi = z[k]
+                pr, pi = zp[k]
+                a1 = (self.fma(-t1, zi, zr), self.fma(t1, zr, zi))
+                b1 = (self.fma(-t3, pi, pr), self.fma(t3, pr, pi))
+                s1 = (self.fma(rho, b1[0], a1[0]), self.fma(rho, b1[1], a1[1]))
+                d1 = (self.fma(-rho, b1[0], a1[0]), self.fma(-rho, b1[1], a1[1]))
+            ur, ui = u[k]
+            vr, vi = u[k + q]
+            out[k] = (self.fma(c1, s1[0], ur), self.fma(c1, s1[1], ui))
+            out[k + 2 * q] = (self.fma(-c1, s1[0], ur), self.fma(-c1, s1[1], ui))
+            # -j (a - b) = c1 * (d1.im, -d1.re)
+            out[k + q] = (self.fma(c1, d1[1], vr), self.fma(-c1, d1[0], vi))
+            out[k + 3 * q] = (self.fma(-c1, d1[1], vr), self.fma(c1, d1[0], vi))
         return out
 
 
