@@ -33,6 +33,23 @@ for n, m in ((2046, 2), (4092, 1)):
         t = _native.Tracker(eng, [24, 6], [1500.0, -100.0], [0.0, 0.0], [777, 5])
         rec, prof = t.process(12, [round(k * n / fs, 6) for k in range(12)], want_profiles=True)
         assert rec["symbol"].shape == (2, 12)
+        ts = np.array([round(k * n / fs, 6) for k in range(12)])
+        for _ in range(9):  # > 80 symbols: bit-phase search and bit emission of the navigation-bit kernel
+            t.process(12, ts)
+            bits = t.integrate_bits(12, ts, ts + 0.001)
+        assert len(bits) == 2 and t.bit_state(0)["processed_pseudosymbol_count"] == 108
         t.close()
+        # pipelined batch stream: three streams, pageable staging
+        gs = _native.GridStream(eng, 2, 1, [24, 0, 5], dop, _native.NON_COHERENT, depth=2)
+        xb = o.synth_iq(2, n, 2, fs, [(25, 1500.0, 777, 0.3, 0.3)])
+        outs = []
+        for k in range(4):
+            if gs.in_flight == 2:
+                outs.append(gs.collect().copy())
+            gs.submit(xb)
+        while gs.in_flight:
+            outs.append(gs.collect().copy())
+        assert all(int(u["argmax"][0, 0, 7]) == 777 for u in outs)
+        gs.close()
     eng.close()
 print("sanitize_small ok")
