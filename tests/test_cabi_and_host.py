@@ -83,3 +83,35 @@ def test_product_synth_matches_oracle_generators():
         assert np.array_equal(synth.synth_iq(9, n, m, n * 1000, planted), o.synth_iq(9, n, m, n * 1000, planted))
     ch = [(7, -2212.7, 0.5, 100, 1.0, 0.005)]
     assert np.array_equal(synth.synth_tracking_iq(4, 2046, 45, 2046000, ch), t.synth_tracking_iq(4, 2046, 45, 2046000, ch))
+
+
+def test_header_is_plain_c_and_links_from_c(native_lib, tmp_path):
+    """include/gypsum_b200.h must be consumable by a C compiler (the boundary is a C ABI, not C++), and a C program
+    linked against the library must see the record layouts the header promises and get a clean error -- not a crash,
+    not a fallback -- when no CUDA device is usable (GPU boxes: the engine comes up instead)."""
+    import subprocess
+
+    from gypsum_b200 import _native
+
+    src = tmp_path / "probe.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "gypsum_b200.h"
+int main(void) {
+    gb200_engine* e = NULL;
+    int rc = gb200_create(0, 2046000, 2046, &e);
+    printf("%d %d %d %d %d %d\n", gb200_abi_version(), (int)sizeof(gb200_cell_record), (int)sizeof(gb200_track_record),
+           (int)sizeof(gb200_acquisition_result), (int)sizeof(gb200_bit_event), rc);
+    if (rc != GB200_OK) { printf("%s\n", gb200_last_error(NULL)); return 0; }
+    gb200_destroy(e);
+    return 0;
+}
+''')
+    exe = tmp_path / "probe"
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", f"-I{inc}", str(src), "-o", str(exe), _native.LIB_PATH,
+                    f"-Wl,-rpath,{os.path.dirname(_native.LIB_PATH)}"], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines()
+    fields = [int(v) for v in out[0].split()]
+    assert fields[1:5] == [32, 96, 32, 32]
+    assert fields[5] == 0 or "no usable CUDA device" in out[1]
