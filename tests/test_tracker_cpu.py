@@ -26,10 +26,14 @@ def load_case(name):
     return z, ch, x
 
 
-@pytest.mark.parametrize("name,limit", [("short", 700), ("long", 1200)])
+@pytest.mark.parametrize("name,limit", [("short", 700), ("long", 1200), ("fs4", 500)])
 def test_oracle_tracker_bit_exact_with_reference(name, limit):
+    """fs4: 4.092 Msps, where the reference keeps its hard-wired 2046 (tracker.py:301-303, :319)."""
     z, ch, x = load_case(name)
     init = z["init"]
+    N, FS = (int(z["n"]), int(z["fs"])) if "n" in z.files else (2046, 2046000)
+    if N != 2046:
+        x = t.synth_tracking_iq(int(z["seed"]), N, int(z["n_ms"]), FS, [ch], float(z["sigma"]))
     tr = t.TrackerOracle(ch[0], init[0], init[1], int(init[2]), FS, N)
     for k in range(min(limit, len(z["rows"]))):
         a, b = t.chunk_times(k, FS, N)

@@ -22,11 +22,11 @@ OUT = os.path.join(ROOT, "tests", "golden")
 N, FS = 2046, 2046000
 
 
-def run(name, seed, n_ms, channel, init, sigma=0.02):
+def run(name, seed, n_ms, channel, init, sigma=0.02, N=N, FS=FS):
     codes = generate_replica_prn_signals()
     sv = channel[0]
     x = t.synth_tracking_iq(seed, N, n_ms, FS, [channel], sigma)
-    sat = GpsSatellite(GpsSatelliteId(sv), codes[GpsSatelliteId(sv)], 2)
+    sat = GpsSatellite(GpsSatelliteId(sv), codes[GpsSatelliteId(sv)], N // 1023)
     params = GpsSatelliteTrackingParameters(satellite=sat, current_doppler_shift=init[0],
                                             current_carrier_wave_phase_shift=init[1],
                                             current_prn_code_phase_shift=init[2], doppler_shifts=[])
@@ -46,7 +46,8 @@ def run(name, seed, n_ms, channel, init, sigma=0.02):
                      ps.start_of_pseudosymbol, ps.end_of_pseudosymbol, trk.phase])
     np.savez_compressed(os.path.join(OUT, f"tracker_{name}.npz"), seed=np.int64(seed), n_ms=np.int64(n_ms),
                         channel=np.array(channel, dtype=np.float64), init=np.array(init, dtype=np.float64),
-                        sigma=np.float64(sigma), rows=np.array(rows, dtype=np.float64), lost_at=np.int64(lost_at))
+                        sigma=np.float64(sigma), rows=np.array(rows, dtype=np.float64), lost_at=np.int64(lost_at),
+                        n=np.int64(N), fs=np.int64(FS))
     r = np.array(rows)
     print(name, "ms", len(rows), "lost_at", lost_at, "final doppler", r[-1, 6], "symbols +/-", (r[:, 3] > 0).sum(), (r[:, 3] < 0).sum())
 
@@ -56,3 +57,6 @@ if __name__ == "__main__":
     run("short", 11, 700, (25, 1500.3, 0.0, 777, 0.3, 0.004), (1500.0, 0.0, 777))
     run("long", 12, 6300, (7, -2212.7, 0.5, 100, 1.0, 0.005), (-2210.0, 0.5, 100))   # crosses the 6 s circularity check
     run("noise", 13, 6100, (3, 800.0, 0.0, 5, 0.0, 0.0), (800.0, 0.0, 5))            # no signal: loses lock at the check
+    # 4.092 Msps: the reference keeps its hard-wired 2046 (tracker.py:301-303, :319) -- SURVEY F12 -- so the code-phase
+    # accumulator wraps at 2046 although a millisecond is 4092 samples; the planted phase stays below 2046
+    run("fs4", 14, 500, (12, 640.4, 0.0, 1501, 0.7, 0.004), (640.0, 0.0, 1501), N=4092, FS=4092000)
