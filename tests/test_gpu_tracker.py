@@ -96,36 +96,6 @@ def test_free_running_matches_reference(engine, name):
     assert rec["locked"].sum() > 0 and rec["locked"][:250].sum() == 0
 
 
-@pytest.mark.xfail(strict=False, reason="4.092 Msps tracking (k_track_channels<4>): golden recorded after the round's GPU "
-                                         "budget was spent, not yet run on hardware; make strict next round")
-def test_free_running_at_4092_ksps_matches_reference(native_lib):
-    """The reference at 4.092 Msps keeps its hard-wired 2046 (tracker.py:301-303, :319; SURVEY F12): the code-phase
-    accumulator wraps at 2046 although a millisecond is 4092 samples.  Same bounds as the 2.046 Msps trajectories."""
-    from gypsum_b200 import _native
-
-    z = np.load(os.path.join(GOLDEN, "tracker_fs4.npz"))
-    n, fs = int(z["n"]), int(z["fs"])
-    ch = z["channel"]
-    ch = (int(ch[0]), ch[1], ch[2], int(ch[3]), ch[4], ch[5])
-    x = t.synth_tracking_iq(int(z["seed"]), n, int(z["n_ms"]), fs, [ch], float(z["sigma"]))
-    init, rows = z["init"], z["rows"]
-    eng = _native.Engine(fs, n)
-    eng.set_replicas(np.stack([o.ca_code(sv) for sv in range(1, 33)]).astype(np.uint8))
-    eng.upload_iq(x)
-    trk = _native.Tracker(eng, [ch[0] - 1], [init[0]], [init[1]], [int(init[2])])
-    tt = np.array([t.chunk_times(k, fs, n)[0] for k in range(len(rows))])
-    rec = trk.process(len(rows), tt)[0]
-    trk.close()
-    eng.close()
-    assert not rec["lost"].any()
-    sym_mismatch = np.flatnonzero(rec["symbol"] != rows[:, 3].astype(int))
-    assert all(abs(rows[k, 0]) <= 1e-4 * np.abs(rows[:, 0]).max() for k in sym_mismatch) and len(sym_mismatch) <= 1
-    assert np.abs(rec["doppler"] - rows[:, 6]).max() <= 5e-3
-    d = np.abs(rec["carrier_phase"] - rows[:, 7])
-    assert np.minimum(d, 2 * np.pi - d).max() <= 2e-3
-    assert np.mean(rec["code_phase"] == rows[:, 8].astype(int)) >= 0.995
-
-
 def test_noise_channel_loses_lock_at_the_six_second_check(engine):
     from gypsum_b200 import _native
 
@@ -222,3 +192,48 @@ def test_tracker_bank_class(engine):
             assert ps.pseudosymbol.as_val() == rec[c, k]["symbol"]
         assert params.current_doppler_shift == rec[c, -1]["doppler"]
         assert len(params.non_coherent_correlation_profiles) == 0
+
+
+_FS4_SCRIPT = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+from gypsum_b200 import _native
+from oracle import gypsum_oracle as o
+from oracle import tracker_oracle as t
+
+z = np.load(os.path.join(sys.argv[1], "tests", "golden", "tracker_fs4.npz"))
+n, fs = int(z["n"]), int(z["fs"])
+ch = z["channel"]
+ch = (int(ch[0]), ch[1], ch[2], int(ch[3]), ch[4], ch[5])
+x = t.synth_tracking_iq(int(z["seed"]), n, int(z["n_ms"]), fs, [ch], float(z["sigma"]))
+init, rows = z["init"], z["rows"]
+eng = _native.Engine(fs, n)
+eng.set_replicas(np.stack([o.ca_code(sv) for sv in range(1, 33)]).astype(np.uint8))
+eng.upload_iq(x)
+trk = _native.Tracker(eng, [ch[0] - 1], [init[0]], [init[1]], [int(init[2])])
+tt = np.array([t.chunk_times(k, fs, n)[0] for k in range(len(rows))])
+rec = trk.process(len(rows), tt)[0]
+assert not rec["lost"].any()
+sym_mismatch = np.flatnonzero(rec["symbol"] != rows[:, 3].astype(int))
+assert all(abs(rows[k, 0]) <= 1e-4 * np.abs(rows[:, 0]).max() for k in sym_mismatch) and len(sym_mismatch) <= 1
+assert np.abs(rec["doppler"] - rows[:, 6]).max() <= 5e-3
+d = np.abs(rec["carrier_phase"] - rows[:, 7])
+assert np.minimum(d, 2 * np.pi - d).max() <= 2e-3
+assert np.mean(rec["code_phase"] == rows[:, 8].astype(int)) >= 0.995
+print("fs4 ok")
+"""
+
+
+@pytest.mark.xfail(strict=False, reason="4.092 Msps tracking (k_track_channels<4>): golden recorded after the round's GPU "
+                                         "budget was spent, not yet run on hardware; make strict next round")
+def test_free_running_at_4092_ksps_matches_reference(native_lib):
+    """The reference at 4.092 Msps keeps its hard-wired 2046 (tracker.py:301-303, :319; SURVEY F12): the code-phase
+    accumulator wraps at 2046 although a millisecond is 4092 samples.  Same bounds as the 2.046 Msps trajectories.
+    Runs in its own process (last test of the last GPU file) so that a fault on this never-exercised path cannot
+    disturb the CUDA context of the other tests."""
+    import subprocess
+    import sys
+
+    proc = subprocess.run([sys.executable, "-c", _FS4_SCRIPT, ROOT], capture_output=True, text=True, timeout=300)
+    assert proc.returncode == 0 and "fs4 ok" in proc.stdout, proc.stderr[-2000:]
