@@ -13,6 +13,11 @@
 //   refine_*          planning / selection kernels of the on-device search (acquisition.py:70-152).
 #include <cstdlib>
 
+// GB_W2048_LAYOUT_B=1 builds k_correlate_w2048 with the experimental row order of warp_fft.cuh (w2048b_*): validated on the
+// host lane emulator (tests/test_emulation.py), not yet measured on hardware; the shipped build keeps 0.
+#ifndef GB_W2048_LAYOUT_B
+#define GB_W2048_LAYOUT_B 0
+#endif
 #include "kernels.cuh"
 #include "ptx_helpers.cuh"
 #include "warp_fft.cuh"
@@ -395,8 +400,17 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
 template <int NW, bool SINGLE_MS>
 __global__ void __launch_bounds__(NW * 32, 1) k_correlate_w2048(const CorrelateArgs a) {
     extern __shared__ __align__(16) float2 smem[];
+#if GB_W2048_LAYOUT_B
+    // the odd-bin half of the replica spectrum sits 64 bytes further: lanes 2i / 2i+1 read the same offset of the two
+    // halves, and the shift puts them on different banks
+    constexpr int kCrepOdd = kFft + 8;
+    float2* crep_s = smem;                      // [1024] even bins, 8 pad, [1024] odd bins
+    float2* tw1_s = crep_s + 2 * kFft + 8;      // [32][32]: W2048^(lane k1)
+#else
+    constexpr int kCrepOdd = kFft;
     float2* crep_s = smem;              // [2][1024]
     float2* tw1_s = crep_s + 2 * kFft;  // [32][32]
+#endif
     float2* tiles = tw1_s + kFft;       // [NW][kTile64F2]
     PairPartial* partial = reinterpret_cast<PairPartial*>(tiles + NW * kTile64F2);  // [NW]
     uint64_t* mbar = reinterpret_cast<uint64_t*>(partial + NW);
@@ -406,6 +420,15 @@ __global__ void __launch_bounds__(NW * 32, 1) k_correlate_w2048(const CorrelateA
 
     uint32_t parity = 0;
     if (threadIdx.x == 0) mbar_init(mbar, 1);
+#if GB_W2048_LAYOUT_B
+    // T[k1][lane] = W2048^(lane k1) gathered from the W2048^n table (lane k1 <= 961)
+    for (int t = threadIdx.x; t < kFft; t += NW * 32) {
+        const int k1 = t >> 5, l = t & 31;
+        tw1_s[pidx(k1, l)] = a.tw2[zpos(l * k1)];
+    }
+    const float sc_b = w2048b_scale(lane);
+    __syncthreads();
+#else
     __syncthreads();
     if (threadIdx.x == 0) {
         mbar_expect_tx(mbar, kFft * sizeof(float2));
@@ -413,6 +436,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_correlate_w2048(const CorrelateA
     }
     mbar_wait(mbar, parity);
     parity ^= 1;
+#endif
     asm volatile("griddepcontrol.wait;" ::: "memory");  // see k_correlate_cells: PDL against doppler_spectra
 
     const int cells_per_group = NW / a.rsplit;
@@ -462,7 +486,12 @@ __global__ void __launch_bounds__(NW * 32, 1) k_correlate_w2048(const CorrelateA
             __syncthreads();
             if (threadIdx.x == 0) {
                 mbar_expect_tx(mbar, 2 * kFft * sizeof(float2));
+#if GB_W2048_LAYOUT_B
+                bulk_g2s(crep_s, a.crep + static_cast<size_t>(prn) * 2 * kFft, kFft * sizeof(float2), mbar);
+                bulk_g2s(crep_s + kCrepOdd, a.crep + static_cast<size_t>(prn) * 2 * kFft + kFft, kFft * sizeof(float2), mbar);
+#else
                 bulk_g2s(crep_s, a.crep + static_cast<size_t>(prn) * 2 * kFft, 2 * kFft * sizeof(float2), mbar);
+#endif
             }
             mbar_wait(mbar, parity);
             parity ^= 1;
@@ -482,6 +511,27 @@ __global__ void __launch_bounds__(NW * 32, 1) k_correlate_w2048(const CorrelateA
                 const int n_iter = SINGLE_MS ? 1 : a.M;
                 for (int it = 0; it < n_iter; ++it) {
                     const float2* __restrict__ p = spec_u + static_cast<size_t>(it * a.s + r) * 2 * kFft;
+#if GB_W2048_LAYOUT_B
+                    {
+                        // bins lane + 32 h + 64 j: the vector of virtual lane (lane >> 1) + 16 h of the half-spectrum of
+                        // parity lane & 1
+                        const float2* __restrict__ ph = p + (lane & 1) * kFft;
+                        const float2* ch = crep_s + (lane & 1) * kCrepOdd;
+                        {
+                            float hr[32], hi[32];
+                            load_mul_vec(hr, hi, lane >> 1, ph, ch);
+                            w2048b_phase1<0>(hi, hr, lane, tw1_s, tile);  // inverse = forward on swapped re/im
+                        }
+                        {
+                            float hr[32], hi[32];
+                            load_mul_vec(hr, hi, (lane >> 1) + 16, ph, ch);
+                            w2048b_phase1<1>(hi, hr, lane, tw1_s, tile);
+                        }
+                    }
+                    __syncwarp();
+                    float re[64], im[64];
+                    w2048b_phase2(im, re, lane, tile, sc_b);
+#else
                     {
                         float hr[32], hi[32];
                         load_mul_vec(hr, hi, lane, p, crep_s);  // even bins
@@ -495,6 +545,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_correlate_w2048(const CorrelateA
                     __syncwarp();
                     float re[64], im[64];
                     w2048_phase2(im, re, lane, tile);
+#endif
                     __syncwarp();  // the tile may be overwritten by the next transform
 #pragma unroll
                     for (int k = 0; k < 32; ++k) acc[k] += gb_mag(re[k], im[k]);
@@ -674,7 +725,8 @@ size_t correlate_smem_bytes(int np) {
 }
 
 size_t correlate_w2048_smem_bytes(int nw) {
-    return (3 * static_cast<size_t>(kFft) + static_cast<size_t>(nw) * kTile64F2) * sizeof(float2) + nw * sizeof(PairPartial) + 16;
+    return (3 * static_cast<size_t>(kFft) + 8 * GB_W2048_LAYOUT_B + static_cast<size_t>(nw) * kTile64F2) * sizeof(float2) +
+           nw * sizeof(PairPartial) + 16;
 }
 
 bool spectra_supports(int s) {
