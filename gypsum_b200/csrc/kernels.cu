@@ -18,6 +18,13 @@
 #ifndef GB_W2048_LAYOUT_B
 #define GB_W2048_LAYOUT_B 0
 #endif
+// GB_SPEC_ALIAS=1 (experimental, unmeasured, off in the shipped build): when every (branch, parity) task of
+// k_doppler_spectra has its own warp (2S <= 8) the transpose tiles reuse the memory of the polyphase rows, which are dead
+// once every warp has its vector in registers: 35 KB instead of 52 KB per 2.046 Msps CTA, and with the register cap of
+// five CTAs per SM the 1312 units of a 32-block batch take two waves instead of three.
+#ifndef GB_SPEC_ALIAS
+#define GB_SPEC_ALIAS 0
+#endif
 #include "kernels.cuh"
 #include "ptx_helpers.cuh"
 #include "warp_fft.cuh"
@@ -70,7 +77,22 @@ __global__ void __launch_bounds__(128) k_replica_spectra(const uint8_t* chips, f
 __host__ __device__ constexpr int spec_warps(int s) { return 2 * s >= 8 ? 8 : 2 * s; }
 constexpr int kCarrierTable = 64;  // >= ceil(N / threads) for every supported rate
 
+__host__ __device__ constexpr bool spec_alias(int s) { return GB_SPEC_ALIAS && 2 * s <= 8; }
+__host__ __device__ constexpr int spec_f2(int s) {  // float2 of rows + tiles
+    return spec_alias(s) ? (s * kFft > spec_warps(s) * kTileF2 ? s * kFft : spec_warps(s) * kTileF2)
+                         : s * kFft + spec_warps(s) * kTileF2;
+}
+
 template <int S>
+#if GB_SPEC_ALIAS
+__global__ void __launch_bounds__(spec_warps(S) * 32, S == 2 ? 5 : 1) k_doppler_spectra(const SpectraArgs a) {
+    constexpr int kSpecWarps = spec_warps(S);
+    constexpr int kSpecThreads = kSpecWarps * 32;
+    extern __shared__ __align__(16) float2 smem[];
+    float2* ypoly = smem;                                       // [S][1024], rows in zpos() order
+    float2* tiles = spec_alias(S) ? smem : smem + S * kFft;     // [kSpecWarps][kTileF2]
+    float2* coarse = smem + spec_f2(S);                         // [kCarrierTable] carrier at samples 0, 256, 512, ...
+#else
 __global__ void __launch_bounds__(spec_warps(S) * 32) k_doppler_spectra(const SpectraArgs a) {
     constexpr int kSpecWarps = spec_warps(S);
     constexpr int kSpecThreads = kSpecWarps * 32;
@@ -78,6 +100,7 @@ __global__ void __launch_bounds__(spec_warps(S) * 32) k_doppler_spectra(const Sp
     float2* ypoly = smem;                          // [S][1024], rows in zpos() order
     float2* tiles = smem + S * kFft;               // [kSpecWarps][kTileF2]
     float2* coarse = tiles + kSpecWarps * kTileF2;  // [kCarrierTable] carrier at samples 0, 256, 512, ...
+#endif
 
     const int unit = blockIdx.x / a.M, i = blockIdx.x % a.M;
     const int b = unit / a.n_doppler, d = unit % a.n_doppler;
@@ -128,6 +151,9 @@ __global__ void __launch_bounds__(spec_warps(S) * 32) k_doppler_spectra(const Sp
         const int r = task >> 1, half = task & 1;
         float re[32], im[32];
         load_vec(re, im, lane, ypoly + r * kFft);
+#if GB_SPEC_ALIAS
+        if (spec_alias(S)) __syncthreads();  // single pass (one task per warp): the rows are dead, the tiles may take their place
+#endif
         if (half) mul_tw2(re, im, lane, a.tw2);
         wfft_phase1(re, im, lane, a.tw1, tile);
         __syncwarp();
@@ -718,7 +744,7 @@ cudaError_t launch_refine_finalize(int n_sv, const RefineState* st, const CellRe
 // launch wrappers
 // ---------------------------------------------------------------------------------------------------------
 size_t spectra_smem_bytes(int s) {
-    return (static_cast<size_t>(s) * kFft + spec_warps(s) * kTileF2 + kCarrierTable) * sizeof(float2);
+    return (static_cast<size_t>(spec_f2(s)) + kCarrierTable) * sizeof(float2);
 }
 size_t correlate_smem_bytes(int np) {
     return (4 * static_cast<size_t>(kFft) + 2 * np * kTileF2) * sizeof(float2) + 2 * np * sizeof(PairPartial) + 16;
