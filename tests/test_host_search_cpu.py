@@ -42,7 +42,8 @@ class OracleEngine:
         return rec
 
     def correlation_profile(self, prn, dop, n_ms, kind):
-        return np.abs(self._profile(prn, dop, n_ms, kind))
+        prof = self._profile(prn, dop, n_ms, kind)
+        return prof if kind == _native.COHERENT else np.abs(prof)
 
 
 class Attrs:
@@ -82,3 +83,42 @@ def test_pass_by_pass_search_reproduces_the_reference_detector(monkeypatch):
     best = det.get_best_doppler_shift_estimation(0.0, 7000.0, x, Attrs, GpsSatelliteId(25))
     assert best.sample_offset_of_correlation_peak == int(best.non_coherent_correlation_profile.argmax()) == 777
     assert best.doppler_shift in doppler_search_bins(0.0, 7000.0)
+
+
+def test_drop_in_utils_wrappers_argument_handling(monkeypatch):
+    """utils.py:59-108 as the host code implements it around the engine: a replica rolled by any number of samples (the
+    tracker rolls by the code phase, tracker.py:286), a trailing partial millisecond (dropped, utils.py:34-38), no whole
+    millisecond at all, the integration-type error -- each compared with the oracle called the reference's way."""
+    import pytest
+
+    from gypsum_b200 import utils
+    from gypsum_b200.utils import (IntegrationType, frequency_domain_correlation,
+                                   integrate_correlation_with_doppler_shifted_prn)
+
+    n, fs = 4092, 4092000
+    eng = OracleEngine(fs, n)
+    ent = {"engine": eng, "codes": {}, "table": []}
+    monkeypatch.setattr(utils.POOL, "get", lambda fs_, n_, device=0: ent)
+
+    class A:
+        samples_per_second, samples_per_prn_transmission = fs, n
+
+    x = o.synth_iq(3, n, 3, fs, [(9, 1250.0, 1001, 0.4, 0.3)])
+    rep = o.replica(9, n)
+    for roll in (0, 1, 3, 4, 1001, n - 1):  # within a chip (4 samples per chip), whole chips, both
+        r = np.roll(rep, roll)
+        want = o.integrate(o.NON_COHERENT, x, fs, n, 1250.0, r)
+        got = integrate_correlation_with_doppler_shifted_prn(IntegrationType.NonCoherent, x, A, 1250.0, r)
+        assert got.dtype == np.float64 and np.abs(got - want).max() <= 1e-9 * want.max(), roll
+    ragged = np.concatenate([x, x[:100]])
+    want = o.integrate(o.COHERENT, x, fs, n, -300.0, rep)
+    got = integrate_correlation_with_doppler_shifted_prn(IntegrationType.Coherent, ragged, A, -300.0, rep)
+    assert got.dtype == np.complex128 and np.abs(got - want).max() <= 1e-9 * np.abs(want).max()
+    empty = integrate_correlation_with_doppler_shifted_prn(IntegrationType.NonCoherent, x[: n - 1], A, 0.0, rep)
+    assert empty.shape == (n,) and not empty.any()
+    one = frequency_domain_correlation(x[:n], np.roll(rep, 6))
+    assert np.abs(one - o.correlate_1ms(x[:n].astype(np.complex128), np.roll(rep, 6))).max() <= 1e-9 * np.abs(one).max()
+    with pytest.raises(ValueError, match="Unexpected integration type"):
+        integrate_correlation_with_doppler_shifted_prn("coherent", x, A, 0.0, rep)
+    with pytest.raises(ValueError):
+        integrate_correlation_with_doppler_shifted_prn(IntegrationType.Coherent, x, A, 0.0, rep * 0.5)  # not +-1 chips
