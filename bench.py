@@ -33,6 +33,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 N = 2046
+WORKLOAD = "config2: 32 PRN x 41 Doppler (+-10 kHz / 500 Hz) x 1 ms non-coherent @ 2.046 Msps complex64"  # both arms
 FS = 2046000
 N_PRN = 32
 DOPPLERS = np.arange(-10000.0, 10001.0, 500.0)  # 41 bins
@@ -158,7 +159,7 @@ def run_reference(args, rank: int, world: int) -> None:
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "config2: 32 PRN x 41 Doppler x 1 ms non-coherent @ 2.046 Msps", "blocks_per_step": 1,
+        "config": {"workload": WORKLOAD, "blocks_per_step": 1,
                    "sample": "each step = one full 32x41 grid over one 1-ms block (bounded sample of the GPU arm's step)"},
         "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": use, "kind": "port",
                          "sample": f"{args.steps} x one 1-ms block, 1312 cells each, PRNs over {use} processes"},
@@ -375,7 +376,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": "config2: 32 PRN x 41 Doppler (+-10 kHz / 500 Hz) x 1 ms non-coherent @ 2.046 Msps complex64",
+                "workload": WORKLOAD,
                 "blocks_per_step": B, "cells_per_block": n_cells, "parallelism": f"blocks sharded over {world} GPU(s), no collective",
                 "l2": f"inputs larger than L2: IQ ring of {ring_blocks} distinct blocks = {ring_blocks * block_bytes >> 20} MiB per GPU, "
                       "a fresh batch every step; replica spectra + twiddles (0.5 MiB) and the spectra scratch stay cache-resident by design",
