@@ -72,6 +72,27 @@ GB_HD inline void track_state_init(TrackState& st, int prn, double doppler, doub
     st.n_cnt = st.p_cnt = 0;
 }
 
+// tracker.py:191-197: the mean of the negative-pole cluster must lie within 6 degrees of the real axis (the reference
+// writes abs() of a bool -- just the comparison).
+GB_HD inline bool track_rot_ok(double mr, double mi) {
+    const double angle = 180.0 - pymod((atan2(mi, mr) / kTau) * 360.0, 180.0);
+    const double centered = angle < 90.0 ? angle : 180.0 - angle;
+    return centered < 6.0;
+}
+// The same decision without the atan2 / fmod chain on almost every millisecond: |mi| against tan(6 deg) |mr| with a guard
+// band of +-0.01 degree, inside which -- and for NaNs and the origin -- the reference arithmetic above decides.
+// EXPERIMENTAL (GB_TRACK_FAST_ANGLE=1, off in the shipped build): equivalence is tested on the host, the kernel variant has
+// not been timed.
+GB_HD inline bool track_rot_ok_fast(double mr, double mi) {
+    const double a = fabs(mi), b = fabs(mr);
+    if (a < 0.10492777752783379 * b) return true;   // tan(5.99 deg)
+    if (a > 0.10528069947757225 * b) return false;  // tan(6.01 deg)
+    return track_rot_ok(mr, mi);
+}
+#ifndef GB_TRACK_FAST_ANGLE
+#define GB_TRACK_FAST_ANGLE 0
+#endif
+
 // tracker.py:157-203.  Called after the current peak was pushed and before the current error is.
 GB_HD inline bool track_is_locked(const TrackState& st) {
     if (st.err_count < kLockWindow) return false;
@@ -91,9 +112,11 @@ GB_HD inline bool track_is_locked(const TrackState& st) {
             pv = st.p_sre2 / st.p_cnt - pm * pm;
         }
         i_ok = (nv + pv) / 2.0 < 2.0;
-        const double angle = 180.0 - pymod((atan2(mi, mr) / kTau) * 360.0, 180.0);
-        const double centered = angle < 90.0 ? angle : 180.0 - angle;
-        rot_ok = centered < 6.0;  // tracker.py:197: abs() of a bool -- just the comparison
+#if GB_TRACK_FAST_ANGLE
+        rot_ok = track_rot_ok_fast(mr, mi);
+#else
+        rot_ok = track_rot_ok(mr, mi);
+#endif
     }
     return var_ok && i_ok && rot_ok;
 }

@@ -215,6 +215,8 @@ void emu_track_update(TrackState* st, const float* elp /* E.re E.im L.re L.im P.
 }
 }
 
+extern "C" int emu_track_rot_ok(double mr, double mi, int fast) { return fast ? track_rot_ok_fast(mr, mi) : track_rot_ok(mr, mi); }
+
 // ---- one-warp pruned inverse FFT-2048 (w2048_phase1/2) ----
 extern "C" void emu_ifft2048_pruned(const float2* y_even, const float2* y_odd, float2* out /*[1024]*/) {
     init_tables();

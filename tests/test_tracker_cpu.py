@@ -87,3 +87,26 @@ def test_scalar_loop_teacher_forced(emu_lib, name):
         assert lost_at == int(z["lost_at"]) == 6000
     else:
         assert lost_at == -1 and locked_ref > 0
+
+
+def test_fast_angle_test_decides_like_the_reference_arithmetic(emu_lib):
+    """track_rot_ok_fast (|mi| vs tan(6 deg)|mr| with a guard band, experimental) == track_rot_ok (the atan2 / modulo
+    arithmetic of tracker.py:191-197) everywhere: random directions, a dense sweep across both 6-degree boundaries in all
+    four quadrants, the axes, the origin, NaN and infinities."""
+    f = emu_lib.emu_track_rot_ok
+    f.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_int]
+    rng = np.random.default_rng(0)
+    cases = [(0.0, 0.0), (-0.0, 0.0), (1.0, 0.0), (-1.0, 0.0), (0.0, 1.0), (0.0, -1.0), (float("nan"), 1.0), (1.0, float("nan")),
+             (float("inf"), 1.0), (-3.0, float("inf"))]
+    cases += [tuple(v) for v in rng.standard_normal((20000, 2)) * np.exp(rng.uniform(-20, 20, (20000, 1)))]
+    for base in (6.0, 174.0, 186.0, 354.0):
+        for d in np.linspace(-0.02, 0.02, 4001):
+            a = np.radians(base + d)
+            r = np.exp(rng.uniform(-5, 5))
+            cases.append((r * np.cos(a), r * np.sin(a)))
+    got_true = 0
+    for mr, mi in cases:
+        slow, fast = f(mr, mi, 0), f(mr, mi, 1)
+        assert slow == fast, (mr, mi)
+        got_true += slow
+    assert 0 < got_true < len(cases)
