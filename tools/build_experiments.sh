@@ -8,4 +8,5 @@ SRC="kernels.cu tracker.cu bits.cu fused.cu engine.cu"
 nvcc $FLAGS -DGB_W2048_LAYOUT_B=1 -o ../exp_layout_b.so $SRC
 nvcc $FLAGS -DGB_SPEC_ALIAS=1 -o ../exp_spec_alias.so $SRC
 nvcc $FLAGS -DGB_W2048_LAYOUT_B=1 -DGB_SPEC_ALIAS=1 -o ../exp_both.so $SRC
+nvcc $FLAGS -DGB_TRACK_FAST_ANGLE=1 -o ../exp_fast_angle.so $SRC
 ls -la ../exp_*.so
