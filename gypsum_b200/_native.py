@@ -109,6 +109,10 @@ class Engine:
         self.samples_per_ms = int(samples_per_ms)
         self.device = int(device)
         self.n_prn = 0
+        # What the engine's single IQ binding currently holds: a caller-chosen tag (e.g. the chunk key the trackers use to
+        # share one upload), cleared by EVERY call that rebinds the IQ -- so no caller can mistake another caller's samples
+        # for its own.
+        self.iq_tag = None
         self._children = weakref.WeakSet()  # trackers / grid streams: they hold device memory tied to this engine
 
     # -- plumbing ------------------------------------------------------------------------------------------
@@ -163,16 +167,22 @@ class Engine:
         self._check(self._lib.gb200_set_replicas(self._h, _ptr(chips), chips.shape[0]), "gb200_set_replicas")
         self.n_prn = chips.shape[0]
 
-    def upload_iq(self, samples: np.ndarray) -> None:
+    def upload_iq(self, samples: np.ndarray, tag=None) -> None:
+        """tag: optional hashable naming these samples; `iq_tag` holds it until the next call that rebinds the IQ."""
         x = np.ascontiguousarray(samples, dtype=np.complex64)
         self._iq_keepalive = x
+        self.iq_tag = None
         self._check(self._lib.gb200_upload_iq(self._h, _ptr(x), x.size), "gb200_upload_iq")
+        self.iq_tag = tag
 
     def upload_iq_ptr(self, host_ptr: int, n_samples: int) -> None:
+        self.iq_tag = None
         self._check(self._lib.gb200_upload_iq(self._h, _P(host_ptr), n_samples), "gb200_upload_iq")
 
-    def bind_iq_device(self, device_ptr: int, n_samples: int) -> None:
+    def bind_iq_device(self, device_ptr: int, n_samples: int, tag=None) -> None:
+        self.iq_tag = None
         self._check(self._lib.gb200_bind_iq_device(self._h, _P(device_ptr), n_samples), "gb200_bind_iq_device")
+        self.iq_tag = tag
 
     # -- the hot path --------------------------------------------------------------------------------------
     def acquire_grid(self, n_blocks: int, ms_per_block: int, prn_idx, doppler_hz, kind: int = NON_COHERENT,
@@ -269,6 +279,7 @@ class GridStream:
             out = np.empty(self.shape, dtype=RECORD_DTYPE)
         elif out.dtype != RECORD_DTYPE or out.shape != self.shape or not out.flags["C_CONTIGUOUS"]:
             raise ValueError("out must be a C-contiguous RECORD_DTYPE array of shape [n_blocks, n_prn, n_doppler]")
+        self._engine.iq_tag = None  # the stream rebinds the engine's IQ to its own slot buffer
         self._engine._check(self._lib.gb200_grid_stream_submit(self._h, ptr, _ptr(out)), "gb200_grid_stream_submit")
         self._pending.append((keep, out))
 

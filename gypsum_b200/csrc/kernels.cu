@@ -13,18 +13,6 @@
 //   refine_*          planning / selection kernels of the on-device search (acquisition.py:70-152).
 #include <cstdlib>
 
-// GB_W2048_LAYOUT_B=1 builds k_correlate_w2048 with the experimental row order of warp_fft.cuh (w2048b_*): validated on the
-// host lane emulator (tests/test_emulation.py), not yet measured on hardware; the shipped build keeps 0.
-#ifndef GB_W2048_LAYOUT_B
-#define GB_W2048_LAYOUT_B 0
-#endif
-// GB_SPEC_ALIAS=1 (experimental, unmeasured, off in the shipped build): when every (branch, parity) task of
-// k_doppler_spectra has its own warp (2S <= 8) the transpose tiles reuse the memory of the polyphase rows, which are dead
-// once every warp has its vector in registers: 35 KB instead of 52 KB per 2.046 Msps CTA, and with the register cap of
-// five CTAs per SM the 1312 units of a 32-block batch take two waves instead of three.
-#ifndef GB_SPEC_ALIAS
-#define GB_SPEC_ALIAS 0
-#endif
 #include "kernels.cuh"
 #include "ptx_helpers.cuh"
 #include "warp_fft.cuh"
@@ -77,14 +65,17 @@ __global__ void __launch_bounds__(128) k_replica_spectra(const uint8_t* chips, f
 __host__ __device__ constexpr int spec_warps(int s) { return 2 * s >= 8 ? 8 : 2 * s; }
 constexpr int kCarrierTable = 64;  // >= ceil(N / threads) for every supported rate
 
-__host__ __device__ constexpr bool spec_alias(int s) { return GB_SPEC_ALIAS && 2 * s <= 8; }
+// When every (branch, parity) task has its own warp (2S <= 8) the transpose tiles take the place of the polyphase rows,
+// which are dead once every warp holds its vector in registers: 35 KB instead of 52 KB per 2.046 Msps CTA and, with the
+// register cap of five CTAs per SM, the 1312 units of a 32-block batch run in two waves instead of three (measured on
+// B200: 30.1 -> 24.0 us per 32-block launch, profiles/ablation_r2.md).
+__host__ __device__ constexpr bool spec_alias(int s) { return 2 * s <= 8; }
 __host__ __device__ constexpr int spec_f2(int s) {  // float2 of rows + tiles
     return spec_alias(s) ? (s * kFft > spec_warps(s) * kTileF2 ? s * kFft : spec_warps(s) * kTileF2)
                          : s * kFft + spec_warps(s) * kTileF2;
 }
 
 template <int S>
-#if GB_SPEC_ALIAS
 __global__ void __launch_bounds__(spec_warps(S) * 32, S == 2 ? 5 : 1) k_doppler_spectra(const SpectraArgs a) {
     constexpr int kSpecWarps = spec_warps(S);
     constexpr int kSpecThreads = kSpecWarps * 32;
@@ -92,15 +83,6 @@ __global__ void __launch_bounds__(spec_warps(S) * 32, S == 2 ? 5 : 1) k_doppler_
     float2* ypoly = smem;                                       // [S][1024], rows in zpos() order
     float2* tiles = spec_alias(S) ? smem : smem + S * kFft;     // [kSpecWarps][kTileF2]
     float2* coarse = smem + spec_f2(S);                         // [kCarrierTable] carrier at samples 0, 256, 512, ...
-#else
-__global__ void __launch_bounds__(spec_warps(S) * 32) k_doppler_spectra(const SpectraArgs a) {
-    constexpr int kSpecWarps = spec_warps(S);
-    constexpr int kSpecThreads = kSpecWarps * 32;
-    extern __shared__ __align__(16) float2 smem[];
-    float2* ypoly = smem;                          // [S][1024], rows in zpos() order
-    float2* tiles = smem + S * kFft;               // [kSpecWarps][kTileF2]
-    float2* coarse = tiles + kSpecWarps * kTileF2;  // [kCarrierTable] carrier at samples 0, 256, 512, ...
-#endif
 
     const int unit = blockIdx.x / a.M, i = blockIdx.x % a.M;
     const int b = unit / a.n_doppler, d = unit % a.n_doppler;
@@ -151,9 +133,7 @@ __global__ void __launch_bounds__(spec_warps(S) * 32) k_doppler_spectra(const Sp
         const int r = task >> 1, half = task & 1;
         float re[32], im[32];
         load_vec(re, im, lane, ypoly + r * kFft);
-#if GB_SPEC_ALIAS
         if (spec_alias(S)) __syncthreads();  // single pass (one task per warp): the rows are dead, the tiles may take their place
-#endif
         if (half) mul_tw2(re, im, lane, a.tw2);
         wfft_phase1(re, im, lane, a.tw1, tile);
         __syncwarp();
@@ -426,17 +406,9 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
 template <int NW, bool SINGLE_MS>
 __global__ void __launch_bounds__(NW * 32, 1) k_correlate_w2048(const CorrelateArgs a) {
     extern __shared__ __align__(16) float2 smem[];
-#if GB_W2048_LAYOUT_B
-    // the odd-bin half of the replica spectrum sits 64 bytes further: lanes 2i / 2i+1 read the same offset of the two
-    // halves, and the shift puts them on different banks
-    constexpr int kCrepOdd = kFft + 8;
-    float2* crep_s = smem;                      // [1024] even bins, 8 pad, [1024] odd bins
-    float2* tw1_s = crep_s + 2 * kFft + 8;      // [32][32]: W2048^(lane k1)
-#else
     constexpr int kCrepOdd = kFft;
     float2* crep_s = smem;              // [2][1024]
     float2* tw1_s = crep_s + 2 * kFft;  // [32][32]
-#endif
     float2* tiles = tw1_s + kFft;       // [NW][kTile64F2]
     PairPartial* partial = reinterpret_cast<PairPartial*>(tiles + NW * kTile64F2);  // [NW]
     uint64_t* mbar = reinterpret_cast<uint64_t*>(partial + NW);
@@ -446,15 +418,6 @@ __global__ void __launch_bounds__(NW * 32, 1) k_correlate_w2048(const CorrelateA
 
     uint32_t parity = 0;
     if (threadIdx.x == 0) mbar_init(mbar, 1);
-#if GB_W2048_LAYOUT_B
-    // T[k1][lane] = W2048^(lane k1) gathered from the W2048^n table (lane k1 <= 961)
-    for (int t = threadIdx.x; t < kFft; t += NW * 32) {
-        const int k1 = t >> 5, l = t & 31;
-        tw1_s[pidx(k1, l)] = a.tw2[zpos(l * k1)];
-    }
-    const float sc_b = w2048b_scale(lane);
-    __syncthreads();
-#else
     __syncthreads();
     if (threadIdx.x == 0) {
         mbar_expect_tx(mbar, kFft * sizeof(float2));
@@ -462,7 +425,6 @@ __global__ void __launch_bounds__(NW * 32, 1) k_correlate_w2048(const CorrelateA
     }
     mbar_wait(mbar, parity);
     parity ^= 1;
-#endif
     asm volatile("griddepcontrol.wait;" ::: "memory");  // see k_correlate_cells: PDL against doppler_spectra
 
     const int cells_per_group = NW / a.rsplit;
@@ -512,12 +474,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_correlate_w2048(const CorrelateA
             __syncthreads();
             if (threadIdx.x == 0) {
                 mbar_expect_tx(mbar, 2 * kFft * sizeof(float2));
-#if GB_W2048_LAYOUT_B
-                bulk_g2s(crep_s, a.crep + static_cast<size_t>(prn) * 2 * kFft, kFft * sizeof(float2), mbar);
-                bulk_g2s(crep_s + kCrepOdd, a.crep + static_cast<size_t>(prn) * 2 * kFft + kFft, kFft * sizeof(float2), mbar);
-#else
                 bulk_g2s(crep_s, a.crep + static_cast<size_t>(prn) * 2 * kFft, 2 * kFft * sizeof(float2), mbar);
-#endif
             }
             mbar_wait(mbar, parity);
             parity ^= 1;
@@ -537,27 +494,6 @@ __global__ void __launch_bounds__(NW * 32, 1) k_correlate_w2048(const CorrelateA
                 const int n_iter = SINGLE_MS ? 1 : a.M;
                 for (int it = 0; it < n_iter; ++it) {
                     const float2* __restrict__ p = spec_u + static_cast<size_t>(it * a.s + r) * 2 * kFft;
-#if GB_W2048_LAYOUT_B
-                    {
-                        // bins lane + 32 h + 64 j: the vector of virtual lane (lane >> 1) + 16 h of the half-spectrum of
-                        // parity lane & 1
-                        const float2* __restrict__ ph = p + (lane & 1) * kFft;
-                        const float2* ch = crep_s + (lane & 1) * kCrepOdd;
-                        {
-                            float hr[32], hi[32];
-                            load_mul_vec(hr, hi, lane >> 1, ph, ch);
-                            w2048b_phase1<0>(hi, hr, lane, tw1_s, tile);  // inverse = forward on swapped re/im
-                        }
-                        {
-                            float hr[32], hi[32];
-                            load_mul_vec(hr, hi, (lane >> 1) + 16, ph, ch);
-                            w2048b_phase1<1>(hi, hr, lane, tw1_s, tile);
-                        }
-                    }
-                    __syncwarp();
-                    float re[64], im[64];
-                    w2048b_phase2(im, re, lane, tile, sc_b);
-#else
                     {
                         float hr[32], hi[32];
                         load_mul_vec(hr, hi, lane, p, crep_s);  // even bins
@@ -571,7 +507,6 @@ __global__ void __launch_bounds__(NW * 32, 1) k_correlate_w2048(const CorrelateA
                     __syncwarp();
                     float re[64], im[64];
                     w2048_phase2(im, re, lane, tile);
-#endif
                     __syncwarp();  // the tile may be overwritten by the next transform
 #pragma unroll
                     for (int k = 0; k < 32; ++k) acc[k] += gb_mag(re[k], im[k]);
@@ -751,7 +686,7 @@ size_t correlate_smem_bytes(int np) {
 }
 
 size_t correlate_w2048_smem_bytes(int nw) {
-    return (3 * static_cast<size_t>(kFft) + 8 * GB_W2048_LAYOUT_B + static_cast<size_t>(nw) * kTile64F2) * sizeof(float2) +
+    return (3 * static_cast<size_t>(kFft) + static_cast<size_t>(nw) * kTile64F2) * sizeof(float2) +
            nw * sizeof(PairPartial) + 16;
 }
 

@@ -391,75 +391,3 @@ GB_HD GB_INLINE void w2048_phase2(float (&re)[64], float (&im)[64], int lane, co
 }
 
 }  // namespace gb
-
-namespace gb {
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Layout B of the one-warp pruned inverse FFT-2048 (EXPERIMENTAL: compiled into the product only with
-// -DGB_W2048_LAYOUT_B=1; validated on the host lane emulator, not yet measured on hardware).  Rows l' = lane + 32 h
-// instead of 2 lane + h: thread `lane` holds, for h = 0, 1, the 32 elements Y[(lane + 32 h) + 64 j''] -- in the
-// existing storage that is the vector of "virtual lane" (lane >> 1) + 16 h of the half-spectrum of parity lane & 1.
-// Twiddle after the FFT-32 over j'':  W2048^((lane + 32 h) k1) = T[k1][lane] * W64^(h k1),  T[k1][lane] =
-// W2048^(lane k1) = tw2[lane k1] (lane k1 <= 961).  For h = 1 the constant W64^k1 = (-j)^a e^(-j phi), |phi| <= pi/4,
-// costs the two FMAs of its tangent form, (v.re + t v.im, v.im - t v.re), the quarter turns being register renames;
-// the remaining real factor cos(phi(k1)) is the same for all 32 upper rows of a phase-2 thread (k1 = its lane) and
-// rides on the first butterflies of the FFT-64, which pair row l' with row l' + 32 (fft64_fwd_hiscale).  Against
-// w2048_phase1<1> (table value x constant, then x data: 8 instructions per element) this is 6.
-// ---------------------------------------------------------------------------------------------------------------------
-#define GB_W2048B_TAN 0.000000000e+00f, 9.849140336e-02f, 1.989123674e-01f, 3.033466836e-01f, 4.142135624e-01f, 5.345111360e-01f, 6.681786379e-01f, 8.206787908e-01f, 1.000000000e+00f, -8.206787908e-01f, -6.681786379e-01f, -5.345111360e-01f, -4.142135624e-01f, -3.033466836e-01f, -1.989123674e-01f, -9.849140336e-02f, 0.000000000e+00f, 9.849140336e-02f, 1.989123674e-01f, 3.033466836e-01f, 4.142135624e-01f, 5.345111360e-01f, 6.681786379e-01f, 8.206787908e-01f, -1.000000000e+00f, -8.206787908e-01f, -6.681786379e-01f, -5.345111360e-01f, -4.142135624e-01f, -3.033466836e-01f, -1.989123674e-01f, -9.849140336e-02f
-// cos(phi(k1)), for reference (w2048b_scale computes it)
-#define GB_W2048B_COS 1.000000000e+00f, 9.951847267e-01f, 9.807852804e-01f, 9.569403357e-01f, 9.238795325e-01f, 8.819212643e-01f, 8.314696123e-01f, 7.730104534e-01f, 7.071067812e-01f, 7.730104534e-01f, 8.314696123e-01f, 8.819212643e-01f, 9.238795325e-01f, 9.569403357e-01f, 9.807852804e-01f, 9.951847267e-01f, 1.000000000e+00f, 9.951847267e-01f, 9.807852804e-01f, 9.569403357e-01f, 9.238795325e-01f, 8.819212643e-01f, 8.314696123e-01f, 7.730104534e-01f, 7.071067812e-01f, 7.730104534e-01f, 8.314696123e-01f, 8.819212643e-01f, 9.238795325e-01f, 9.569403357e-01f, 9.807852804e-01f, 9.951847267e-01f
-
-GB_HD GB_INLINE constexpr int w2048b_quarter(int k1) { return k1 <= 8 ? 0 : (k1 < 24 ? 1 : 2); }
-GB_HD GB_INLINE float w2048b_scale(int k1) {  // cos(phi(k1)) for the thread that owns column k1 in phase 2 (once per kernel)
-    const double turns = static_cast<double>(k1) / 32.0 - 0.5 * w2048b_quarter(k1);  // phi / pi
-#if defined(__CUDA_ARCH__)
-    return static_cast<float>(cospi(turns));
-#else
-    return static_cast<float>(__builtin_cos(3.14159265358979323846 * turns));
-#endif
-}
-
-// twb[pidx(k1, lane)] = W2048^(lane k1)
-template <int H>
-GB_HD GB_INLINE void w2048b_phase1(float (&re)[32], float (&im)[32], int lane, const float2* twb, float2* tile) {
-    constexpr float kTan[32] = {GB_W2048B_TAN};
-    fft32_fwd(re, im);
-    float2* row = tile + (H * 32 + lane) * kT64Stride;  // physical row l' = lane + 32 H
-#pragma unroll
-    for (int kp = 0; kp < 16; ++kp) {
-        float2 w0, w1;
-        ld_pair(twb + 2 * (kp * 32 + lane), w0, w1);
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int k1 = 2 * kp + q;
-            float2 v = make_float2(re[k1], im[k1]);
-            if (k1 != 0) v = cmul(v, q ? w1 : w0);
-            if (H == 1 && k1 != 0) {
-                // v * (1 - j t) * (-j)^a with the quarter turn folded into the operand signs of the two FMAs (a store
-                // cannot negate, an FMA operand can)
-                const float t = kTan[k1];
-                const int a = w2048b_quarter(k1);
-                if (k1 == 16) v = make_float2(v.y, -v.x);  // t = 0, a = 1
-                else if (a == 0) v = make_float2(fmaf(t, v.y, v.x), fmaf(-t, v.x, v.y));
-                else if (a == 1) v = make_float2(fmaf(-t, v.x, v.y), fmaf(-t, v.y, -v.x));
-                else v = make_float2(fmaf(-t, v.y, -v.x), fmaf(t, v.x, -v.y));
-            }
-            row[k1] = v;
-        }
-    }
-}
-
-// Phase 2: thread `lane` owns column k1 = lane: gathers the 64 rows in natural order, FFT-64 over l' with the factor of
-// the upper 32 rows folded in.  Afterwards re/im[k2] = X[lane + 32 k2]; only k2 < 32 are meaningful.
-GB_HD GB_INLINE void w2048b_phase2(float (&re)[64], float (&im)[64], int lane, const float2* tile, float sc) {
-#pragma unroll
-    for (int p = 0; p < 64; ++p) {
-        const float2 e = tile[p * kT64Stride + lane];
-        re[p] = e.x;
-        im[p] = e.y;
-    }
-    fft64_fwd_hiscale(re, im, sc);
-}
-
-}  // namespace gb

@@ -179,9 +179,8 @@ class GpsSatelliteTracker:
         self._push_host_edits()
         samples = receiver_samples_chunk.samples
         key = (id(samples), float(receiver_samples_chunk.start_time))
-        if self._ent.get("last_chunk") != key:  # several trackers usually share one chunk: upload it once
-            self._eng.upload_iq(samples)
-            self._ent["last_chunk"] = key
+        if self._eng.iq_tag != key:  # several trackers usually share one chunk: upload it once.  The tag lives in the
+            self._eng.upload_iq(samples, tag=key)  # engine wrapper and every other upload / bind clears it
         got = self._native.process(1, [receiver_samples_chunk.start_time], want_profiles=self.keep_correlation_profiles)
         rec, prof = (got[0][0, 0], got[1][0, 0]) if self.keep_correlation_profiles else (got[0, 0], None)
         if int(rec["symbol"]) == 0:
@@ -216,7 +215,6 @@ class TrackerBank:
         x = np.ascontiguousarray(samples, dtype=np.complex64)
         n_ms = x.size // self.samples_per_ms
         self.engine.upload_iq(x[: n_ms * self.samples_per_ms])
-        self._ent["last_chunk"] = None
         return self.native.process(n_ms, start_times, want_profiles)
 
     def integrate_bits(self, start_times, end_times) -> list:

@@ -96,7 +96,9 @@ class TrackerOracle:
         self.errors.append(error)
         out = dict(peak=peak, strength=strength, symbol=symbol, error=error, disc=float(disc), locked=locked,
                    code_phase=self.code_phase, start=start_time + delay, end=end_time + delay, early=complex(early),
-                   late=complex(late), peak_offset=k)
+                   late=complex(late), peak_offset=k,
+                   # tracker.py:352-353 appends the loop state to the histories BEFORE the 6-second adjustment below
+                   doppler_hist=self.doppler, carrier_phase_hist=self.carrier_phase)
         if start_time - self.last_circularity_check >= 6:  # tracker.py:370-387
             self.last_circularity_check = start_time
             pk = np.array(self.peaks)

@@ -240,35 +240,6 @@ extern "C" void emu_ifft2048_pruned(const float2* y_even, const float2* y_odd, f
     }
 }
 
-// ---- layout B of the one-warp pruned inverse FFT-2048 (w2048b_phase1/2, fft64_fwd_hiscale) ----
-// Built from the same stored tables as the kernel would use: twb[k1][lane] = tw2[lane * k1].
-extern "C" void emu_ifft2048_pruned_b(const float2* y_even, const float2* y_odd, float2* out /*[1024]*/) {
-    init_tables();
-    std::vector<float2> tile(kTile64F2), twb(1024);
-    for (int k1 = 0; k1 < 32; ++k1)
-        for (int l = 0; l < 32; ++l) twb[pidx(k1, l)] = g_tw2[zpos(l * k1)];
-    static float ra[32][32], ia[32][32], rb[32][32], ib[32][32];
-    for (int lane = 0; lane < 32; ++lane) {
-        const float2* half = (lane & 1) ? y_odd : y_even;  // parity of the bins lane + 32 h + 64 j
-        for (int j = 0; j < 32; ++j) {
-            const float2 a = half[(lane >> 1) + 32 * j], b = half[(lane >> 1) + 16 + 32 * j];
-            ra[lane][j] = a.x;
-            ia[lane][j] = a.y;
-            rb[lane][j] = b.x;
-            ib[lane][j] = b.y;
-        }
-    }
-    for (int lane = 0; lane < 32; ++lane) {  // inverse = forward on swapped re/im
-        w2048b_phase1<0>(ia[lane], ra[lane], lane, twb.data(), tile.data());
-        w2048b_phase1<1>(ib[lane], rb[lane], lane, twb.data(), tile.data());
-    }
-    for (int lane = 0; lane < 32; ++lane) {
-        float re[64], im[64];
-        w2048b_phase2(im, re, lane, tile.data(), w2048b_scale(lane));
-        for (int k2 = 0; k2 < 32; ++k2) out[lane + 32 * k2] = make_float2(re[k2], im[k2]);
-    }
-}
-
 // ---- navigation bit integration (bits_core.cuh) on the host ----
 #include "../../gypsum_b200/csrc/bits_core.cuh"
 extern "C" {

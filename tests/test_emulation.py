@@ -56,23 +56,3 @@ def test_one_warp_pruned_ifft2048(emu_lib):
     y[0::2], y[1::2] = ye, yo
     ref = (np.fft.ifft(y) * 2048)[:1024]
     assert np.abs(out - ref).max() <= 5e-7 * np.abs(ref).max()
-
-
-def test_one_warp_pruned_ifft2048_layout_b(emu_lib):
-    """The experimental row order l' = lane + 32 h (w2048b_phase1/2 + fft64_fwd_hiscale: quarter turns as renames,
-    tangent-form constants, the cosine folded into the first FFT-64 butterflies) computes the same transform, to the
-    same accuracy, from the same stored half-spectra and twiddle table as the layout in use."""
-    rng = np.random.default_rng(6)
-    ye = (rng.standard_normal(1024) + 1j * rng.standard_normal(1024)).astype(np.complex64)
-    yo = (rng.standard_normal(1024) + 1j * rng.standard_normal(1024)).astype(np.complex64)
-    out = np.zeros(1024, np.complex64)
-    cur = np.zeros(1024, np.complex64)
-    emu_lib.emu_ifft2048_pruned_b(ye.ctypes.data_as(ctypes.c_void_p), yo.ctypes.data_as(ctypes.c_void_p),
-                                  out.ctypes.data_as(ctypes.c_void_p))
-    emu_lib.emu_ifft2048_pruned(ye.ctypes.data_as(ctypes.c_void_p), yo.ctypes.data_as(ctypes.c_void_p),
-                                cur.ctypes.data_as(ctypes.c_void_p))
-    y = np.empty(2048, complex)
-    y[0::2], y[1::2] = ye, yo
-    ref = (np.fft.ifft(y) * 2048)[:1024]
-    assert np.abs(out - ref).max() <= 5e-7 * np.abs(ref).max()
-    assert np.abs(out - ref).max() <= 1.5 * np.abs(cur - ref).max()

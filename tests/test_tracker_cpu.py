@@ -26,7 +26,7 @@ def load_case(name):
     return z, ch, x
 
 
-@pytest.mark.parametrize("name,limit", [("short", 700), ("long", 1200), ("fs4", 500)])
+@pytest.mark.parametrize("name,limit", [("short", 700), ("long", 1200), ("fs4", 500), ("adjust", 6100)])
 def test_oracle_tracker_bit_exact_with_reference(name, limit):
     """fs4: 4.092 Msps, where the reference keeps its hard-wired 2046 (tracker.py:301-303, :319)."""
     z, ch, x = load_case(name)
@@ -39,8 +39,11 @@ def test_oracle_tracker_bit_exact_with_reference(name, limit):
         a, b = t.chunk_times(k, FS, N)
         r = tr.step(x[k * N:(k + 1) * N], a, b)
         mine = np.array([r["peak"].real, r["peak"].imag, r["strength"], r["symbol"], r["error"], r["disc"], r["doppler"],
-                         r["carrier_phase"], r["code_phase"], r["start"], r["end"], tr.phase], dtype=np.float64)
+                         r["carrier_phase"], r["code_phase"], r["start"], r["end"], tr.phase, r["doppler_hist"],
+                         r["carrier_phase_hist"]], dtype=np.float64)
         assert np.array_equal(mine, z["rows"][k]), k
+    if name == "adjust":  # the 6-second nudge fired: histories hold the value before it, current_* the value after
+        assert z["rows"][6000, 6] - z["rows"][6000, 12] == 5.0 and z["rows"][6000, 7] != z["rows"][6000, 13]
 
 
 @pytest.mark.parametrize("name", ["short", "long", "noise"])

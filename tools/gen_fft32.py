@@ -21,7 +21,6 @@ class Emitter:
         self.lines = []
         self.n = 0
         self.flops = 0
-        self.scaled = set()
 
     def tmp(self, expr):
         name = f"t{self.n}"
@@ -39,28 +38,14 @@ class Emitter:
         self.flops += 1
         return self.tmp(f"fmaf({self.lit(const)}, {x}, {y})")
 
-    # complex values are (re_name, im_name) string pairs.  Names listed in self.scaled stand for sc * name: the
-    # "hiscale" variant folds a real run-time factor on the upper half of the inputs into the first butterflies, which
-    # in a decimation-in-time transform always pair x[n] with x[n + N/2].
+    # complex values are (re_name, im_name) string pairs
     def add(self, a, b):
-        if a[0] in self.scaled:
-            a, b = b, a
-        if b[0] in self.scaled:
-            assert a[0] not in self.scaled
-            self.flops += 2
-            return (self.tmp(f"fmaf(sc, {b[0]}, {a[0]})"), self.tmp(f"fmaf(sc, {b[1]}, {a[1]})"))
         return (self.tmp(f"{a[0]} + {b[0]}"), self.tmp(f"{a[1]} + {b[1]}"))
 
     def sub(self, a, b):
-        if b[0] in self.scaled:
-            assert a[0] not in self.scaled
-            self.flops += 2
-            return (self.tmp(f"fmaf(-sc, {b[0]}, {a[0]})"), self.tmp(f"fmaf(-sc, {b[1]}, {a[1]})"))
-        assert a[0] not in self.scaled
         return (self.tmp(f"{a[0]} - {b[0]}"), self.tmp(f"{a[1]} - {b[1]}"))
 
     def mul_neg_j(self, a):  # a * (-j) = (im, -re)
-        assert a[0] not in self.scaled
         return (a[1], f"(-{a[0]})")
 
     def mulw(self, a, num, den):
@@ -143,24 +128,18 @@ class Emitter:
         return out
 
 
-def emit(n, hiscale=False):
+def emit(n):
     e = Emitter()
     # snapshot inputs so the in-place writes below cannot alias
     xin = []
     for i in range(n):
         e.lines.append(f"    const float xr{i} = re[{i}], xi{i} = im[{i}];")
         xin.append((f"xr{i}", f"xi{i}"))
-        if hiscale and i >= n // 2:
-            e.scaled.update((f"xr{i}", f"xi{i}"))
     y = e.fft(xin)
     for k in range(n):
         e.lines.append(f"    re[{k}] = {y[k][0]}; im[{k}] = {y[k][1]};")
-    if hiscale:
-        head = (f"// forward DFT-{n} of (x[0..{n // 2 - 1}], sc * x[{n // 2}..{n - 1}]): the real factor rides on the first butterflies for free\n"
-                f"GB_HD GB_INLINE void fft{n}_fwd_hiscale(float (&re)[{n}], float (&im)[{n}], float sc) {{\n")
-    else:
-        head = (f"// forward DFT-{n}, X[k] = sum_n x[n] exp(-2 pi i n k / {n}); ~{e.flops} flops\n"
-                f"GB_HD GB_INLINE void fft{n}_fwd(float (&re)[{n}], float (&im)[{n}]) {{\n")
+    head = (f"// forward DFT-{n}, X[k] = sum_n x[n] exp(-2 pi i n k / {n}); ~{e.flops} flops\n"
+            f"GB_HD GB_INLINE void fft{n}_fwd(float (&re)[{n}], float (&im)[{n}]) {{\n")
     return head + "\n".join(e.lines) + "\n}\n"
 
 
@@ -168,7 +147,6 @@ def main():
     out = ["// GENERATED by tools/gen_fft32.py -- do not edit.", "#pragma once", '#include "gb_common.cuh"', ""]
     for n in (4, 8, 16, 32, 64):
         out.append(emit(n))
-    out.append(emit(64, hiscale=True))
     path = os.path.join(ROOT, "gypsum_b200", "csrc", "fft32_gen.cuh")
     with open(path, "w") as f:
         f.write("\n".join(out))

@@ -43,7 +43,10 @@ def run(name, seed, n_ms, channel, init, sigma=0.02, N=N, FS=FS):
         rows.append([pk.real, pk.imag, params.correlation_peak_strengths_rolling_buffer[-1], ps.pseudosymbol.as_val(),
                      params.carrier_wave_phase_errors[-1], params.discriminators[-2], params.current_doppler_shift,
                      params.current_carrier_wave_phase_shift, params.current_prn_code_phase_shift,
-                     ps.start_of_pseudosymbol, ps.end_of_pseudosymbol, trk.phase])
+                     ps.start_of_pseudosymbol, ps.end_of_pseudosymbol, trk.phase,
+                     # what the reference APPENDS to its histories (tracker.py:352-353): the values before the 6-second
+                     # constellation adjustment of :370-387, which only the current_* fields above include
+                     params.doppler_shifts[-1], params.carrier_wave_phases[-1]])
     np.savez_compressed(os.path.join(OUT, f"tracker_{name}.npz"), seed=np.int64(seed), n_ms=np.int64(n_ms),
                         channel=np.array(channel, dtype=np.float64), init=np.array(init, dtype=np.float64),
                         sigma=np.float64(sigma), rows=np.array(rows, dtype=np.float64), lost_at=np.int64(lost_at),
@@ -59,4 +62,6 @@ if __name__ == "__main__":
     run("noise", 13, 6100, (3, 800.0, 0.0, 5, 0.0, 0.0), (800.0, 0.0, 5))            # no signal: loses lock at the check
     # 4.092 Msps: the reference keeps its hard-wired 2046 (tracker.py:301-303, :319) -- SURVEY F12 -- so the code-phase
     # accumulator wraps at 2046 although a millisecond is 4092 samples; the planted phase stays below 2046
+    # weak signal: circularity 0.89 at the 6-second check -> the -+5 Hz / +-pi/2 nudge of tracker.py:380-387 fires
+    run("adjust", 21, 6100, (9, 432.1, 0.0, 300, 0.4, 0.0016), (430.0, 0.0, 300))
     run("fs4", 14, 500, (12, 640.4, 0.0, 1501, 0.7, 0.004), (640.0, 0.0, 1501), N=4092, FS=4092000)
