@@ -21,14 +21,17 @@ RECORD_DTYPE = np.dtype(
 assert RECORD_DTYPE.itemsize == 32
 TRACK_DTYPE = np.dtype(
     [("doppler", "<f8"), ("carrier_phase", "<f8"), ("error", "<f8"), ("disc", "<f8"), ("phase_acc", "<f8"),
-     ("peak_re", "<f4"), ("peak_im", "<f4"), ("strength", "<f4"), ("early_re", "<f4"), ("early_im", "<f4"),
+     ("doppler_hist", "<f8"), ("carrier_phase_hist", "<f8"), ("peak_re", "<f4"), ("peak_im", "<f4"), ("strength", "<f4"), ("early_re", "<f4"), ("early_im", "<f4"),
      ("late_re", "<f4"), ("late_im", "<f4"), ("code_phase", "<i4"), ("symbol", "<i4"), ("locked", "<i4"), ("lost", "<i4"),
      ("peak_offset", "<i4"), ("reserved0", "<i4"), ("reserved1", "<i4")]
 )
-assert TRACK_DTYPE.itemsize == 96
+assert TRACK_DTYPE.itemsize == 112
 ACQ_DTYPE = np.dtype([("doppler", "<f8"), ("strength", "<f8"), ("probe_re", "<f4"), ("probe_im", "<f4"),
                       ("code_phase", "<i4"), ("reserved", "<i4")])
 assert ACQ_DTYPE.itemsize == 32
+BEST_DTYPE = np.dtype([("doppler", "<f8"), ("strength", "<f8"), ("peak", "<f4"), ("code_phase", "<i4"), ("bin", "<i4"),
+                       ("reserved", "<i4")])  # gb200_best_record
+assert BEST_DTYPE.itemsize == 32
 
 # every symbol include/gypsum_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
@@ -43,6 +46,14 @@ SYMBOLS = {
     "gb200_bind_iq_device": (C.c_int, [_P, _P, C.c_int64]),
     "gb200_acquire_grid": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P]),
     "gb200_acquire_grid_device": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P]),
+    "gb200_acquire_grid_host": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P]),
+    "gb200_acquire_grid_best": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P]),
+    "gb200_acquire_grid_best_device": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P]),
+    "gb200_ring_create": (C.c_int, [_P, C.c_int, C.POINTER(_P)]),
+    "gb200_ring_destroy": (C.c_int, [_P]),
+    "gb200_ring_append": (C.c_int, [_P, _P, C.c_int]),
+    "gb200_ring_bind_newest": (C.c_int, [_P, C.c_int]),
+    "gb200_ring_appended": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "gb200_acquire_cells": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P]),
     "gb200_detect": (C.c_int, [_P, C.c_int, _P, C.c_int, _P]),
     "gb200_correlation_profile": (C.c_int, [_P, C.c_int, C.c_double, C.c_int, C.c_int, _P]),
@@ -53,6 +64,10 @@ SYMBOLS = {
     "gb200_tracker_get_state": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                           C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "gb200_tracker_set_state": (C.c_int, [_P, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int32]),
+    "gb200_tracker_create_pool": (C.c_int, [_P, C.c_int, C.POINTER(_P)]),
+    "gb200_tracker_reset_channel": (C.c_int, [_P, C.c_int, C.c_int32, C.c_double, C.c_double, C.c_int32]),
+    "gb200_tracker_process_channels": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, C.c_int, _P, _P]),
+    "gb200_tracker_undo_channel": (C.c_int, [_P, C.c_int]),
     "gb200_grid_stream_create": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "gb200_grid_stream_submit": (C.c_int, [_P, _P, _P]),
     "gb200_grid_stream_collect": (C.c_int, [_P]),
@@ -85,7 +100,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.gb200_abi_version() != 1:
+        if lib.gb200_abi_version() != 2:
             raise ImportError("libgypsum_b200.so ABI version mismatch; rebuild")
         _lib = lib
     return _lib
@@ -202,6 +217,50 @@ class Engine:
         )
         return out
 
+    def acquire_grid_host(self, iq, n_blocks: int, ms_per_block: int, prn_idx, doppler_hz, kind: int = NON_COHERENT,
+                          out: np.ndarray | None = None) -> np.ndarray:
+        """upload + grid + records back in ONE call, replayed as a CUDA graph per shape (latency-bound callers).
+        iq: complex64 array of n_blocks * ms_per_block * N samples, or an int host address of such a buffer."""
+        prn = np.ascontiguousarray(prn_idx, dtype=np.int32)
+        dop = np.ascontiguousarray(doppler_hz, dtype=np.float64)
+        if isinstance(iq, (int, np.integer)):
+            keep, ptr = None, _P(int(iq))
+        else:
+            keep = np.ascontiguousarray(iq, dtype=np.complex64)
+            if keep.size < n_blocks * ms_per_block * self.samples_per_ms:
+                raise ValueError("not enough samples for the grid")
+            ptr = _ptr(keep)
+        if out is None:
+            out = np.empty((n_blocks, prn.size, dop.size), dtype=RECORD_DTYPE)
+        elif out.dtype != RECORD_DTYPE or out.shape != (n_blocks, prn.size, dop.size) or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("out must be a C-contiguous RECORD_DTYPE array of shape [n_blocks, n_prn, n_doppler]")
+        self.iq_tag = None
+        self._check(
+            self._lib.gb200_acquire_grid_host(self._h, ptr, n_blocks, ms_per_block, _ptr(prn), prn.size, _ptr(dop), dop.size,
+                                              kind, _ptr(out)),
+            "gb200_acquire_grid_host",
+        )
+        return out
+
+    def acquire_grid_best(self, n_blocks: int, ms_per_block: int, prn_idx, doppler_hz, kind: int = NON_COHERENT) -> np.ndarray:
+        """acquisition.py:179-189 per (block, prn) row: BEST_DTYPE [n_blocks, n_prn]."""
+        prn = np.ascontiguousarray(prn_idx, dtype=np.int32)
+        dop = np.ascontiguousarray(doppler_hz, dtype=np.float64)
+        out = np.empty((n_blocks, prn.size), dtype=BEST_DTYPE)
+        self._check(
+            self._lib.gb200_acquire_grid_best(self._h, n_blocks, ms_per_block, _ptr(prn), prn.size, _ptr(dop), dop.size, kind,
+                                              _ptr(out)),
+            "gb200_acquire_grid_best",
+        )
+        return out
+
+    def acquire_grid_best_device(self, n_blocks, ms_per_block, prn: np.ndarray, dop: np.ndarray, kind: int, out_device_ptr: int):
+        self._check(
+            self._lib.gb200_acquire_grid_best_device(self._h, n_blocks, ms_per_block, _ptr(prn), prn.size, _ptr(dop), dop.size,
+                                                     kind, _P(out_device_ptr)),
+            "gb200_acquire_grid_best_device",
+        )
+
     def acquire_grid_device(self, n_blocks, ms_per_block, prn: np.ndarray, dop: np.ndarray, kind: int, out_device_ptr: int):
         """prn (int32) / dop (float64) must be contiguous arrays kept alive by the caller; enqueue only."""
         self._check(
@@ -300,8 +359,91 @@ class GridStream:
             pass
 
 
+class Ring:
+    """Device-resident rolling window of the newest milliseconds (gb200_ring_*; receiver.py:68,100,219)."""
+
+    def __init__(self, engine: Engine, capacity_ms: int):
+        self._engine = engine
+        self._lib = engine._lib
+        self.capacity_ms = int(capacity_ms)
+        self._h = _P()
+        engine._check(self._lib.gb200_ring_create(engine._h, self.capacity_ms, C.byref(self._h)), "gb200_ring_create")
+        engine._children.add(self)
+
+    def append(self, samples) -> None:
+        """samples: complex64[n_ms * N] (whole milliseconds)."""
+        x = np.ascontiguousarray(samples, dtype=np.complex64)
+        n = self._engine.samples_per_ms
+        if x.size == 0 or x.size % n:
+            raise ValueError("append whole milliseconds")
+        self._engine._check(self._lib.gb200_ring_append(self._h, _ptr(x), x.size // n), "gb200_ring_append")
+        if isinstance(self._engine.iq_tag, tuple) and self._engine.iq_tag[:1] == ("ring",):
+            self._engine.iq_tag = None  # a binding into this ring no longer names the newest samples
+
+    @property
+    def appended_ms(self) -> int:
+        n = C.c_int64()
+        self._engine._check(self._lib.gb200_ring_appended(self._h, C.byref(n)), "gb200_ring_appended")
+        return n.value
+
+    def bind_newest(self, n_ms: int) -> None:
+        """The engine's IQ := the newest n_ms milliseconds, in place."""
+        tag = ("ring", id(self), self.appended_ms, int(n_ms))
+        if self._engine.iq_tag == tag:
+            return
+        self._engine.iq_tag = None
+        self._engine._check(self._lib.gb200_ring_bind_newest(self._h, int(n_ms)), "gb200_ring_bind_newest")
+        self._engine.iq_tag = tag
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and getattr(self._engine, "_h", None):
+            self._lib.gb200_ring_destroy(self._h)
+            self._engine.iq_tag = None
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Tracker:
     """A bank of tracking channels on one engine (gb200_tracker_*).  Channels consume the engine's loaded IQ."""
+
+    @classmethod
+    def pool(cls, engine: Engine, capacity: int) -> "Tracker":
+        """`capacity` idle channel slots (gb200_tracker_create_pool); seed them with reset_channel."""
+        self = cls.__new__(cls)
+        self._engine = engine
+        self._lib = engine._lib
+        self.n_channels = int(capacity)
+        self._h = _P()
+        engine._check(self._lib.gb200_tracker_create_pool(engine._h, int(capacity), C.byref(self._h)), "gb200_tracker_create_pool")
+        engine._children.add(self)
+        return self
+
+    def reset_channel(self, channel: int, prn_idx: int, doppler: float, carrier_phase: float, code_phase: int) -> None:
+        self._engine._check(self._lib.gb200_tracker_reset_channel(self._h, int(channel), int(prn_idx), float(doppler),
+                                                                  float(carrier_phase), int(code_phase)),
+                            "gb200_tracker_reset_channel")
+
+    def process_channels(self, channels, n_ms: int, start_times, want_profiles: bool = False, keep_undo: bool = False):
+        """gb200_tracker_process for a subset, one launch: records [len(channels), n_ms] (and profiles)."""
+        sel = np.ascontiguousarray(channels, dtype=np.int32)
+        ts = np.ascontiguousarray(start_times, dtype=np.float64)
+        if ts.shape != (n_ms,):
+            raise ValueError("start_times must hold one timestamp per millisecond")
+        out = np.empty((sel.size, n_ms), dtype=TRACK_DTYPE)
+        prof = np.empty((sel.size, n_ms, self._engine.samples_per_ms), dtype=np.float32) if want_profiles else None
+        self._engine._check(
+            self._lib.gb200_tracker_process_channels(self._h, sel.size, _ptr(sel), n_ms, _ptr(ts), int(bool(keep_undo)),
+                                                     _ptr(out), None if prof is None else _ptr(prof)),
+            "gb200_tracker_process_channels")
+        return (out, prof) if want_profiles else out
+
+    def undo_channel(self, channel: int) -> None:
+        self._engine._check(self._lib.gb200_tracker_undo_channel(self._h, int(channel)), "gb200_tracker_undo_channel")
 
     def __init__(self, engine: Engine, prn_idx, doppler_hz, carrier_phase, code_phase):
         self._engine = engine

@@ -71,13 +71,20 @@ class GpsSatelliteDetector:
     def _prepare(self, satellite_ids, antenna_data, stream_attributes):
         fs = int(stream_attributes.samples_per_second)
         n = int(stream_attributes.samples_per_prn_transmission)
+        ent = POOL.get(fs, n)
+        idx = POOL.ensure_table(ent, [self._chips(s, n) for s in satellite_ids])
+        eng = ent["engine"]
+        if hasattr(antenna_data, "bind") and hasattr(antenna_data, "n_ms"):
+            # antenna_sample_provider.DeviceWindow: the samples are already on the device (receiver.py:219 without the copy)
+            n_ms = int(antenna_data.n_ms)
+            if n_ms == 0:
+                raise ValueError("need at least one whole millisecond of samples")
+            antenna_data.bind()
+            return eng, idx, n, n_ms
         data = np.ascontiguousarray(antenna_data, dtype=np.complex64)
         n_ms = data.size // n
         if n_ms == 0:
             raise ValueError("need at least one whole millisecond of samples")
-        ent = POOL.get(fs, n)
-        idx = POOL.ensure_table(ent, [self._chips(s, n) for s in satellite_ids])
-        eng = ent["engine"]
         eng.upload_iq(data[: n_ms * n])
         return eng, idx, n, n_ms
 

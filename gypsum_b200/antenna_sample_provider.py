@@ -141,3 +141,56 @@ class RollingSampleWindow:
             return self._buf[: k * self.n]
         start = self.count % self.window_ms
         return self._buf[start * self.n:(start + self.window_ms) * self.n]
+
+
+class DeviceSampleRing:
+    """receiver.py:68,100,219 with the window on the GPU (gb200_ring_*): `append(chunk)` uploads the new millisecond once
+    and returns the chunk tagged with its place in the ring; GpsSatelliteTracker.process_samples and
+    GpsSatelliteDetector.detect_satellites_in_antenna_data recognise tagged chunks / `window()` and read the samples where
+    they already are instead of uploading them again (one 8*N-byte copy per millisecond in total, whatever the number of
+    tracked satellites; no 10-ms re-upload per acquisition scan)."""
+
+    def __init__(self, stream_attributes, window_ms: int = 10, device: int = 0):
+        from gypsum_b200 import _native
+        from gypsum_b200.utils import POOL
+
+        self.n = int(stream_attributes.samples_per_prn_transmission)
+        self.window_ms = int(window_ms)
+        self._ent = POOL.get(int(stream_attributes.samples_per_second), self.n, device)
+        self.native = _native.Ring(self._ent["engine"], self.window_ms)
+        self.count = 0
+
+    def append(self, chunk: AntennaSampleChunk) -> AntennaSampleChunk:
+        x = np.asarray(chunk.samples)
+        if x.shape != (self.n,):
+            raise ValueError(f"expected one millisecond ({self.n} samples)")
+        self.native.append(x)
+        chunk.device_ring = self
+        chunk.ring_index = self.count
+        self.count += 1
+        return chunk
+
+    def holds_newest(self, chunk) -> bool:
+        return getattr(chunk, "device_ring", None) is self and chunk.ring_index == self.count - 1
+
+    def __len__(self) -> int:
+        return min(self.count, self.window_ms)
+
+    def is_full(self) -> bool:
+        return self.count >= self.window_ms
+
+    def window(self) -> "DeviceWindow":
+        """The newest len(self) milliseconds, oldest first -- what receiver.py:219 concatenates for the detector."""
+        return DeviceWindow(self, len(self))
+
+
+class DeviceWindow:
+    """A view of the newest `n_ms` milliseconds of a DeviceSampleRing; accepted by the detector in place of the ndarray."""
+
+    def __init__(self, ring: DeviceSampleRing, n_ms: int):
+        self.ring = ring
+        self.n_ms = int(n_ms)
+        self.size = self.n_ms * ring.n
+
+    def bind(self) -> None:
+        self.ring.native.bind_newest(self.n_ms)

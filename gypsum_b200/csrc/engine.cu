@@ -109,11 +109,25 @@ struct gb200_engine {
     int fused = -1;  // acquire_cells kernel choice: -1 automatic, 0 doppler_spectra + correlate_cells, 1 fused block-per-cell
     bool detect_fused = true;  // gb200_detect: fused block-per-cell kernel (every cell has its own Doppler)
     bool fused_configured = false;
+    DevBuf<BestRecord> d_best;
+    PinnedBuf<BestRecord> h_best;
+    // gb200_acquire_grid_host: one CUDA graph (copy-in, doppler_spectra, correlate_cells, copy-out) per grid shape
+    struct HostGraph {
+        cudaGraphExec_t exec = nullptr;
+        int n_blocks = 0, M = 0, P = 0, D = 0, kind = 0, seen = 0;
+        std::vector<double> dop;
+        std::vector<int> prn;
+        const void *iq_dev = nullptr, *rec_dev = nullptr, *iq_stage = nullptr, *rec_stage = nullptr, *spec = nullptr;
+        cudaStream_t stream = nullptr;
+    } hg;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[2];
     size_t ev_used[2] = {0, 0};
     std::string err;
 
     ~gb200_engine() {
+        if (hg.exec) cudaGraphExecDestroy(hg.exec);
+        d_best.release();
+        h_best.release();
         tw1.release();
         tw2.release();
         crep.release();
@@ -150,7 +164,12 @@ struct gb200_engine {
 struct gb200_tracker {
     gb200_engine* e = nullptr;
     int n_channels = 0;
-    DevBuf<TrackState> states;
+    std::vector<char> seeded;     // pool slots that hold a channel (gb200_tracker_create seeds all)
+    std::vector<char> undo_ok;    // shadow[c] holds channel c's state before its last keep_undo launch
+    std::vector<int> sel_cache;   // what d_sel currently holds
+    DevBuf<TrackState> states, shadow;
+    DevBuf<int> d_sel;
+    PinnedBuf<int> h_sel;
     DevBuf<TrackMsRecord> d_out;
     DevBuf<double> d_times;
     DevBuf<float> d_prof;
@@ -186,7 +205,18 @@ struct gb200_grid_stream {
     long long head = 0, tail = 0;  // batches submitted / collected
 };
 
+// Device-resident rolling window of the newest milliseconds; every millisecond is stored at slot k and at slot
+// k + capacity, so the newest n <= capacity milliseconds are contiguous whatever the write position.
+struct gb200_ring {
+    gb200_engine* e = nullptr;
+    int capacity = 0;
+    int64_t appended = 0;
+    DevBuf<float2> buf;        // [2 * capacity][N]
+    PinnedBuf<float2> h_stage;  // staging for pageable callers
+};
+
 static_assert(sizeof(gb200_track_record) == sizeof(TrackMsRecord), "ABI track record and device record must match");
+static_assert(sizeof(gb200_best_record) == sizeof(BestRecord), "ABI best record and device record must match");
 static_assert(sizeof(gb200_bit_event) == sizeof(BitEvent), "ABI bit event and device event must match");
 
 #define GB_FAIL(e, code, ...)                        \
@@ -683,7 +713,8 @@ int gb200_upload_iq(gb200_engine* e, const float* iq_host, int64_t n_samples) {
 int gb200_bind_iq_device(gb200_engine* e, const void* iq_device, int64_t n_samples) {
     if (!e) return GB200_EINVAL;
     if (!iq_device || n_samples < 0) GB_FAIL(e, GB200_EINVAL, "bad IQ buffer");
-    if (reinterpret_cast<uintptr_t>(iq_device) % 8 != 0) GB_FAIL(e, GB200_EINVAL, "IQ buffer must be 8-byte aligned");
+    // the fused acquisition kernel stages the IQ with cp.async.bulk and the tracking kernel with 16-byte cp.async
+    if (reinterpret_cast<uintptr_t>(iq_device) % 16 != 0) GB_FAIL(e, GB200_EINVAL, "IQ buffer must be 16-byte aligned");
     e->iq = static_cast<const float2*>(iq_device);
     e->iq_samples = n_samples;
     return GB200_OK;
@@ -708,6 +739,212 @@ int gb200_acquire_grid(gb200_engine* e, int n_blocks, int M, const int32_t* prn_
     int rc = run_grid(e, n_blocks, M, prn_idx, P, dop, D, kind, e->d_records.p);
     if (rc) return rc;
     return fetch_records(e, n, out_host);
+}
+
+// acquisition.py:179-189 per (block, prn) row on the device: the grid, then one reduction kernel over its records.
+int gb200_acquire_grid_best_device(gb200_engine* e, int n_blocks, int M, const int32_t* prn_idx, int P, const double* dop, int D,
+                                   int kind, void* out_device) {
+    if (!e) return GB200_EINVAL;
+    if (!out_device) GB_FAIL(e, GB200_EINVAL, "null output");
+    GB_CUDA(e, cudaSetDevice(e->device));
+    if (n_blocks < 1 || P < 1 || D < 1) GB_FAIL(e, GB200_EINVAL, "empty grid");
+    const size_t n = static_cast<size_t>(n_blocks) * P * D;
+    GB_CUDA(e, e->d_records.ensure(n));
+    int rc = run_grid(e, n_blocks, M, prn_idx, P, dop, D, kind, e->d_records.p);
+    if (rc) return rc;
+    GB_CUDA(e, launch_best_bins(n_blocks * P, D, e->N, e->d_records.p, e->d_doppler.p, static_cast<BestRecord*>(out_device),
+                                e->stream));
+    e->launches++;
+    return GB200_OK;
+}
+
+int gb200_acquire_grid_best(gb200_engine* e, int n_blocks, int M, const int32_t* prn_idx, int P, const double* dop, int D,
+                            int kind, gb200_best_record* out_host) {
+    if (!e) return GB200_EINVAL;
+    if (!out_host) GB_FAIL(e, GB200_EINVAL, "null output");
+    GB_CUDA(e, cudaSetDevice(e->device));
+    if (n_blocks < 1 || P < 1 || D < 1) GB_FAIL(e, GB200_EINVAL, "empty grid");
+    const size_t n = static_cast<size_t>(n_blocks) * P;
+    GB_CUDA(e, cudaStreamSynchronize(e->stream));  // h_best may still be in flight
+    GB_CUDA(e, e->d_best.ensure(n));
+    GB_CUDA(e, e->h_best.ensure(n));
+    int rc = gb200_acquire_grid_best_device(e, n_blocks, M, prn_idx, P, dop, D, kind, e->d_best.p);
+    if (rc) return rc;
+    GB_CUDA(e, cudaMemcpyAsync(e->h_best.p, e->d_best.p, n * sizeof(BestRecord), cudaMemcpyDeviceToHost, e->stream));
+    GB_CUDA(e, cudaStreamSynchronize(e->stream));
+    memcpy(out_host, e->h_best.p, n * sizeof(BestRecord));
+    return GB200_OK;
+}
+
+// Host to host in one call.  The first call of a shape runs eagerly (it may have to upload the axes and grow buffers,
+// which synchronise); the second captures {copy-in, doppler_spectra, correlate_cells, copy-out} into a CUDA graph; from
+// then on a call is: 16 KB memcpy into pinned staging, one cudaGraphLaunch, one stream synchronise, memcpy out.
+int gb200_acquire_grid_host(gb200_engine* e, const float* iq_host, int n_blocks, int M, const int32_t* prn_idx, int P,
+                            const double* dop, int D, int kind, gb200_cell_record* out_host) {
+    if (!e) return GB200_EINVAL;
+    if (!iq_host || !out_host) GB_FAIL(e, GB200_EINVAL, "null buffer");
+    if (n_blocks < 1 || M < 1 || P < 1 || D < 1 || !prn_idx || !dop) GB_FAIL(e, GB200_EINVAL, "empty grid");
+    GB_CUDA(e, cudaSetDevice(e->device));
+    const size_t n_iq = static_cast<size_t>(n_blocks) * M * e->N, n_rec = static_cast<size_t>(n_blocks) * P * D;
+    const size_t spec_bytes = unit_floats2(e, M) * D * sizeof(float2) * n_blocks;
+    static const bool graphs = env_int("GB200_GRAPH", 1) != 0;
+    if (!graphs || e->timing || spec_bytes > e->spec_budget_bytes) {  // several scratch batches / per-kernel events: plain path
+        int rc = gb200_upload_iq(e, iq_host, static_cast<int64_t>(n_iq));
+        if (rc) return rc;
+        return gb200_acquire_grid(e, n_blocks, M, prn_idx, P, dop, D, kind, out_host);
+    }
+    GB_CUDA(e, cudaStreamSynchronize(e->stream));  // the pinned staging buffers may still be in flight
+    GB_CUDA(e, e->iq_own.ensure(n_iq));
+    GB_CUDA(e, e->h_iq.ensure(n_iq));
+    GB_CUDA(e, e->d_records.ensure(n_rec));
+    GB_CUDA(e, e->h_records.ensure(n_rec));
+    memcpy(e->h_iq.p, iq_host, n_iq * sizeof(float2));
+    e->iq = e->iq_own.p;
+    e->iq_samples = static_cast<int64_t>(n_iq);
+
+    auto& g = e->hg;
+    const bool same = g.seen && g.n_blocks == n_blocks && g.M == M && g.P == P && g.D == D && g.kind == kind &&
+                      g.iq_dev == e->iq_own.p && g.rec_dev == e->d_records.p && g.iq_stage == e->h_iq.p &&
+                      g.rec_stage == e->h_records.p && g.spec == e->spec.p && g.stream == e->stream &&
+                      memcmp(g.dop.data(), dop, sizeof(double) * D) == 0 && memcmp(g.prn.data(), prn_idx, sizeof(int) * P) == 0;
+    auto enqueue = [&]() -> int {
+        GB_CUDA(e, cudaMemcpyAsync(e->iq_own.p, e->h_iq.p, n_iq * sizeof(float2), cudaMemcpyHostToDevice, e->stream));
+        int rc = run_grid(e, n_blocks, M, prn_idx, P, dop, D, kind, e->d_records.p);
+        if (rc) return rc;
+        GB_CUDA(e, cudaMemcpyAsync(e->h_records.p, e->d_records.p, n_rec * sizeof(CellRecord), cudaMemcpyDeviceToHost, e->stream));
+        return GB200_OK;
+    };
+    if (same && g.exec) {
+        GB_CUDA(e, cudaGraphLaunch(g.exec, e->stream));
+        e->launches += 2;
+    } else if (same && !g.exec && g.seen == 1) {
+        // second call of this shape: the axes are on the device and every buffer has its size, so nothing below synchronises
+        g.seen = 2;  // capture is attempted once per shape
+        GB_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue();
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+        if (rc == GB200_OK && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&g.exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (rc != GB200_OK || ce != cudaSuccess || !g.exec) {
+            cudaGetLastError();
+            g.exec = nullptr;
+            rc = enqueue();  // capture unavailable: stay on the eager path for this shape
+            if (rc) return rc;
+        } else {
+            GB_CUDA(e, cudaGraphLaunch(g.exec, e->stream));
+        }
+    } else {
+        if (!same) {
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+            g.exec = nullptr;
+        }
+        int rc = enqueue();
+        if (rc) return rc;
+        if (!same) {
+            g.n_blocks = n_blocks;
+            g.M = M;
+            g.P = P;
+            g.D = D;
+            g.kind = kind;
+            g.dop.assign(dop, dop + D);
+            g.prn.assign(prn_idx, prn_idx + P);
+            g.iq_dev = e->iq_own.p;
+            g.rec_dev = e->d_records.p;
+            g.iq_stage = e->h_iq.p;
+            g.rec_stage = e->h_records.p;
+            g.spec = e->spec.p;
+            g.stream = e->stream;
+            g.seen = 1;
+        }
+    }
+    GB_CUDA(e, cudaStreamSynchronize(e->stream));
+    memcpy(out_host, e->h_records.p, n_rec * sizeof(CellRecord));
+    return GB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// device-resident rolling sample window (receiver.py:68,100,219)
+// ---------------------------------------------------------------------------------------------------------
+int gb200_ring_create(gb200_engine* e, int capacity_ms, gb200_ring** out) {
+    if (!e) return GB200_EINVAL;
+    if (!out) GB_FAIL(e, GB200_EINVAL, "null output");
+    *out = nullptr;
+    if (capacity_ms < 1) GB_FAIL(e, GB200_EINVAL, "ring capacity must be at least one millisecond");
+    GB_CUDA(e, cudaSetDevice(e->device));
+    gb200_ring* r = new gb200_ring;
+    r->e = e;
+    r->capacity = capacity_ms;
+    cudaError_t ce = r->buf.ensure(static_cast<size_t>(2) * capacity_ms * e->N);
+    if (ce != cudaSuccess) {
+        delete r;
+        cudaGetLastError();
+        GB_FAIL(e, GB200_ECUDA, "ring allocation failed: %s", cudaGetErrorString(ce));
+    }
+    *out = r;
+    return GB200_OK;
+}
+
+int gb200_ring_destroy(gb200_ring* r) {
+    if (!r) return GB200_OK;
+    gb200_engine* e = r->e;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    if (e->iq >= r->buf.p && e->iq < r->buf.p + r->buf.cap) {  // the engine was reading the ring: unbind
+        e->iq = nullptr;
+        e->iq_samples = 0;
+    }
+    r->buf.release();
+    r->h_stage.release();
+    delete r;
+    return GB200_OK;
+}
+
+int gb200_ring_append(gb200_ring* r, const float* iq_host, int n_ms) {
+    if (!r) return GB200_EINVAL;
+    gb200_engine* e = r->e;
+    if (!iq_host || n_ms < 1) GB_FAIL(e, GB200_EINVAL, "need at least one whole millisecond of samples");
+    if (n_ms > r->capacity) GB_FAIL(e, GB200_EINVAL, "%d ms do not fit a ring of %d ms", n_ms, r->capacity);
+    GB_CUDA(e, cudaSetDevice(e->device));
+    const size_t N = static_cast<size_t>(e->N);
+    const float2* src = reinterpret_cast<const float2*>(iq_host);
+    if (!is_pinned_host(iq_host)) {
+        GB_CUDA(e, cudaStreamSynchronize(e->stream));  // staging buffer may still be in flight
+        GB_CUDA(e, r->h_stage.ensure(N * n_ms));
+        memcpy(r->h_stage.p, iq_host, N * n_ms * sizeof(float2));
+        src = r->h_stage.p;
+    }
+    int done = 0;
+    while (done < n_ms) {
+        const int slot = static_cast<int>((r->appended + done) % r->capacity);
+        const int run = std::min(n_ms - done, r->capacity - slot);
+        float2* lo = r->buf.p + static_cast<size_t>(slot) * N;
+        float2* hi = lo + static_cast<size_t>(r->capacity) * N;
+        GB_CUDA(e, cudaMemcpyAsync(lo, src + static_cast<size_t>(done) * N, run * N * sizeof(float2), cudaMemcpyHostToDevice,
+                                   e->stream));
+        GB_CUDA(e, cudaMemcpyAsync(hi, lo, run * N * sizeof(float2), cudaMemcpyDeviceToDevice, e->stream));
+        done += run;
+    }
+    r->appended += n_ms;
+    return GB200_OK;
+}
+
+int gb200_ring_bind_newest(gb200_ring* r, int n_ms) {
+    if (!r) return GB200_EINVAL;
+    gb200_engine* e = r->e;
+    if (n_ms < 1 || n_ms > r->capacity || n_ms > r->appended)
+        GB_FAIL(e, GB200_EINVAL, "the ring holds %lld of at most %d ms; %d asked for",
+                static_cast<long long>(std::min<int64_t>(r->appended, r->capacity)), r->capacity, n_ms);
+    const int first = static_cast<int>((r->appended - n_ms) % r->capacity);
+    e->iq = r->buf.p + static_cast<size_t>(first) * e->N;
+    e->iq_samples = static_cast<int64_t>(n_ms) * e->N;
+    return GB200_OK;
+}
+
+int gb200_ring_appended(const gb200_ring* r, int64_t* total_ms) {
+    if (!r || !total_ms) return GB200_EINVAL;
+    *total_ms = r->appended;
+    return GB200_OK;
 }
 
 int gb200_acquire_cells(gb200_engine* e, int n_cells, const int32_t* prn_idx, const double* dop, const int32_t* probe,
@@ -1002,6 +1239,8 @@ int gb200_tracker_create(gb200_engine* e, int n_channels, const int32_t* prn_idx
     gb200_tracker* t = new gb200_tracker;
     t->e = e;
     t->n_channels = n_channels;
+    t->seeded.assign(n_channels, 1);
+    t->undo_ok.assign(n_channels, 0);
     std::vector<TrackState> init(n_channels);
     for (int c = 0; c < n_channels; ++c) {
         memset(&init[c], 0, sizeof(TrackState));
@@ -1023,6 +1262,9 @@ int gb200_tracker_destroy(gb200_tracker* t) {
     cudaSetDevice(t->e->device);
     cudaStreamSynchronize(t->e->stream);
     t->states.release();
+    t->shadow.release();
+    t->d_sel.release();
+    t->h_sel.release();
     t->d_out.release();
     t->d_times.release();
     t->d_prof.release();
@@ -1040,7 +1282,10 @@ int gb200_tracker_destroy(gb200_tracker* t) {
     return GB200_OK;
 }
 
-static int tracker_launch(gb200_tracker* t, int n_ms, const double* start_times, TrackMsRecord* out_dev, float* prof_dev) {
+// One launch of k_track_channels.  sel (host, may be null = every channel in order): the n_sel channels to advance; CTA i
+// writes records out_dev[i * n_ms ...].  keep_undo: the kernel also stores every launched channel's previous state.
+static int tracker_launch(gb200_tracker* t, int n_sel, const int32_t* sel, int n_ms, const double* start_times,
+                          TrackMsRecord* out_dev, float* prof_dev, bool keep_undo) {
     gb200_engine* e = t->e;
     if (n_ms < 1 || !start_times) GB_FAIL(e, GB200_EINVAL, "need at least one whole millisecond of samples");
     if (!e->iq) GB_FAIL(e, GB200_ESTATE, "no IQ loaded (gb200_upload_iq / gb200_bind_iq_device)");
@@ -1048,14 +1293,46 @@ static int tracker_launch(gb200_tracker* t, int n_ms, const double* start_times,
         GB_FAIL(e, GB200_EINVAL, "need %lld samples, %lld loaded", static_cast<long long>(n_ms) * e->N,
                 static_cast<long long>(e->iq_samples));
     if (reinterpret_cast<uintptr_t>(e->iq) % 16 != 0) GB_FAIL(e, GB200_EINVAL, "IQ buffer must be 16-byte aligned for tracking");
-    GB_CUDA(e, cudaStreamSynchronize(e->stream));  // h_times may still be in flight
-    GB_CUDA(e, t->d_times.ensure(n_ms));
-    GB_CUDA(e, t->h_times.ensure(n_ms));
-    memcpy(t->h_times.p, start_times, sizeof(double) * n_ms);
-    GB_CUDA(e, cudaMemcpyAsync(t->d_times.p, t->h_times.p, sizeof(double) * n_ms, cudaMemcpyHostToDevice, e->stream));
+    if (sel) {
+        for (int i = 0; i < n_sel; ++i) {
+            if (sel[i] < 0 || sel[i] >= t->n_channels) GB_FAIL(e, GB200_EINVAL, "channel %d out of range", sel[i]);
+            if (!t->seeded[sel[i]]) GB_FAIL(e, GB200_ESTATE, "channel %d was never seeded (gb200_tracker_reset_channel)", sel[i]);
+            for (int j = 0; j < i; ++j)
+                if (sel[j] == sel[i]) GB_FAIL(e, GB200_EINVAL, "channel %d listed twice", sel[i]);
+        }
+    } else {
+        for (int c = 0; c < t->n_channels; ++c)
+            if (!t->seeded[c]) GB_FAIL(e, GB200_ESTATE, "channel %d was never seeded (gb200_tracker_reset_channel)", c);
+    }
     TrackArgs a{};
+    if (n_ms == 1) {
+        a.start_times = nullptr;  // a single millisecond's start time travels in the kernel arguments
+        a.t0_single = start_times[0];
+    } else {
+        GB_CUDA(e, cudaStreamSynchronize(e->stream));  // h_times may still be in flight
+        GB_CUDA(e, t->d_times.ensure(n_ms));
+        GB_CUDA(e, t->h_times.ensure(n_ms));
+        memcpy(t->h_times.p, start_times, sizeof(double) * n_ms);
+        GB_CUDA(e, cudaMemcpyAsync(t->d_times.p, t->h_times.p, sizeof(double) * n_ms, cudaMemcpyHostToDevice, e->stream));
+        a.start_times = t->d_times.p;
+    }
+    if (sel) {
+        const bool cached = static_cast<int>(t->sel_cache.size()) == n_sel && memcmp(t->sel_cache.data(), sel, sizeof(int) * n_sel) == 0;
+        if (!cached) {  // the subset rarely changes between calls: upload it only when it did
+            GB_CUDA(e, cudaStreamSynchronize(e->stream));
+            GB_CUDA(e, t->d_sel.ensure(n_sel));
+            GB_CUDA(e, t->h_sel.ensure(n_sel));
+            memcpy(t->h_sel.p, sel, sizeof(int) * n_sel);
+            GB_CUDA(e, cudaMemcpyAsync(t->d_sel.p, t->h_sel.p, sizeof(int) * n_sel, cudaMemcpyHostToDevice, e->stream));
+            t->sel_cache.assign(sel, sel + n_sel);
+        }
+        a.channel_idx = t->d_sel.p;
+    }
+    if (keep_undo) {
+        GB_CUDA(e, t->shadow.ensure(t->n_channels));
+        a.shadow = t->shadow.p;
+    }
     a.iq = e->iq;
-    a.start_times = t->d_times.p;
     a.states = t->states.p;
     a.out = out_dev;
     a.profiles = prof_dev;
@@ -1067,9 +1344,10 @@ static int tracker_launch(gb200_tracker* t, int n_ms, const double* start_times,
     a.N = e->N;
     a.s = e->s;
     a.n_ms = n_ms;
-    a.n_channels = t->n_channels;
+    a.n_channels = sel ? n_sel : t->n_channels;
     GB_CUDA(e, launch_track_channels(a, e->stream));
     e->launches++;
+    for (int i = 0; i < a.n_channels; ++i) t->undo_ok[sel ? sel[i] : i] = keep_undo ? 1 : 0;
     return GB200_OK;
 }
 
@@ -1078,17 +1356,17 @@ int gb200_tracker_process_device(gb200_tracker* t, int n_ms, const double* start
     gb200_engine* e = t->e;
     if (!out_device) GB_FAIL(e, GB200_EINVAL, "null output");
     GB_CUDA(e, cudaSetDevice(e->device));
-    return tracker_launch(t, n_ms, start_times, static_cast<TrackMsRecord*>(out_device), nullptr);
+    return tracker_launch(t, t->n_channels, nullptr, n_ms, start_times, static_cast<TrackMsRecord*>(out_device), nullptr, false);
 }
 
-int gb200_tracker_process(gb200_tracker* t, int n_ms, const double* start_times, gb200_track_record* out_host,
-                          float* profiles_host) {
-    if (!t) return GB200_EINVAL;
+static int tracker_process_host(gb200_tracker* t, int n_sel, const int32_t* sel, int n_ms, const double* start_times,
+                                bool keep_undo, gb200_track_record* out_host, float* profiles_host) {
     gb200_engine* e = t->e;
     if (!out_host) GB_FAIL(e, GB200_EINVAL, "null output");
     GB_CUDA(e, cudaSetDevice(e->device));
     if (n_ms < 1) GB_FAIL(e, GB200_EINVAL, "need at least one whole millisecond of samples");
-    const size_t n = static_cast<size_t>(t->n_channels) * n_ms;
+    if (n_sel < 1) GB_FAIL(e, GB200_EINVAL, "no channels");
+    const size_t n = static_cast<size_t>(n_sel) * n_ms;
     GB_CUDA(e, t->d_out.ensure(n));
     GB_CUDA(e, t->h_out.ensure(n));
     const size_t np = profiles_host ? n * e->N : 0;
@@ -1097,14 +1375,79 @@ int gb200_tracker_process(gb200_tracker* t, int n_ms, const double* start_times,
         GB_CUDA(e, t->h_prof.ensure(np));
     }
     t->last_n_ms = 0;
-    int rc = tracker_launch(t, n_ms, start_times, t->d_out.p, np ? t->d_prof.p : nullptr);
+    int rc = tracker_launch(t, n_sel, sel, n_ms, start_times, t->d_out.p, np ? t->d_prof.p : nullptr, keep_undo);
     if (rc) return rc;
-    t->last_n_ms = n_ms;
+    if (!sel) t->last_n_ms = n_ms;  // gb200_tracker_integrate_bits reads [channel][n_ms] of the whole bank
     GB_CUDA(e, cudaMemcpyAsync(t->h_out.p, t->d_out.p, n * sizeof(TrackMsRecord), cudaMemcpyDeviceToHost, e->stream));
     if (np) GB_CUDA(e, cudaMemcpyAsync(t->h_prof.p, t->d_prof.p, np * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     GB_CUDA(e, cudaStreamSynchronize(e->stream));
     memcpy(out_host, t->h_out.p, n * sizeof(TrackMsRecord));
     if (np) memcpy(profiles_host, t->h_prof.p, np * sizeof(float));
+    return GB200_OK;
+}
+
+int gb200_tracker_process(gb200_tracker* t, int n_ms, const double* start_times, gb200_track_record* out_host,
+                          float* profiles_host) {
+    if (!t) return GB200_EINVAL;
+    return tracker_process_host(t, t->n_channels, nullptr, n_ms, start_times, false, out_host, profiles_host);
+}
+
+int gb200_tracker_process_channels(gb200_tracker* t, int n_sel, const int32_t* channels, int n_ms, const double* start_times,
+                                   int keep_undo, gb200_track_record* out_host, float* profiles_host) {
+    if (!t) return GB200_EINVAL;
+    if (!channels) GB_FAIL(t->e, GB200_EINVAL, "null channel list");
+    return tracker_process_host(t, n_sel, channels, n_ms, start_times, keep_undo != 0, out_host, profiles_host);
+}
+
+int gb200_tracker_undo_channel(gb200_tracker* t, int channel) {
+    if (!t) return GB200_EINVAL;
+    gb200_engine* e = t->e;
+    if (channel < 0 || channel >= t->n_channels) GB_FAIL(e, GB200_EINVAL, "channel %d out of range", channel);
+    if (!t->undo_ok[channel]) GB_FAIL(e, GB200_ESTATE, "channel %d has no kept state to go back to", channel);
+    GB_CUDA(e, cudaSetDevice(e->device));
+    GB_CUDA(e, cudaMemcpyAsync(t->states.p + channel, t->shadow.p + channel, sizeof(TrackState), cudaMemcpyDeviceToDevice, e->stream));
+    t->undo_ok[channel] = 0;
+    return GB200_OK;
+}
+
+int gb200_tracker_create_pool(gb200_engine* e, int capacity, gb200_tracker** out) {
+    if (!e) return GB200_EINVAL;
+    if (!out) GB_FAIL(e, GB200_EINVAL, "null output");
+    *out = nullptr;
+    if (capacity < 1) GB_FAIL(e, GB200_EINVAL, "no channels");
+    if (e->s != 2 && e->s != 4) GB_FAIL(e, GB200_EINVAL, "tracking needs 2046 or 4092 samples per ms (reference tracker.py:301 hard-wires 2046)");
+    GB_CUDA(e, cudaSetDevice(e->device));
+    GB_CUDA(e, configure_track_kernel());
+    gb200_tracker* t = new gb200_tracker;
+    t->e = e;
+    t->n_channels = capacity;
+    t->seeded.assign(capacity, 0);
+    t->undo_ok.assign(capacity, 0);
+    cudaError_t ce = t->states.ensure(capacity);
+    if (ce == cudaSuccess) ce = cudaMemset(t->states.p, 0, sizeof(TrackState) * capacity);
+    if (ce != cudaSuccess) {
+        delete t;
+        cudaGetLastError();
+        GB_FAIL(e, GB200_ECUDA, "tracker state allocation failed: %s", cudaGetErrorString(ce));
+    }
+    *out = t;
+    return GB200_OK;
+}
+
+int gb200_tracker_reset_channel(gb200_tracker* t, int channel, int32_t prn_idx, double doppler_hz, double carrier_phase,
+                                int32_t code_phase) {
+    if (!t) return GB200_EINVAL;
+    gb200_engine* e = t->e;
+    if (channel < 0 || channel >= t->n_channels) GB_FAIL(e, GB200_EINVAL, "channel %d out of range", channel);
+    if (prn_idx < 0 || prn_idx >= e->n_prn) GB_FAIL(e, GB200_EINVAL, "prn index %d out of range", prn_idx);
+    GB_CUDA(e, cudaSetDevice(e->device));
+    GB_CUDA(e, cudaStreamSynchronize(e->stream));
+    std::vector<TrackState> init(1);
+    memset(init.data(), 0, sizeof(TrackState));
+    track_state_init(init[0], prn_idx, doppler_hz, carrier_phase, code_phase);
+    GB_CUDA(e, cudaMemcpy(t->states.p + channel, init.data(), sizeof(TrackState), cudaMemcpyHostToDevice));
+    t->seeded[channel] = 1;
+    t->undo_ok[channel] = 0;
     return GB200_OK;
 }
 
@@ -1139,7 +1482,9 @@ int gb200_tracker_set_state(gb200_tracker* t, int channel, double doppler_hz, do
     st.carrier_phase = carrier_phase;
     st.phase_acc = phase_acc;
     st.code_phase = code_phase;
+    st.lost = 0;  // the reference tracker object keeps processing after it raised LostSatelliteLockError
     GB_CUDA(e, cudaMemcpy(t->states.p + channel, &st, head, cudaMemcpyHostToDevice));
+    t->undo_ok[channel] = 0;
     return GB200_OK;
 }
 

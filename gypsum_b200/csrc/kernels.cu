@@ -653,6 +653,38 @@ __global__ void k_refine_finalize(int n_sv, const RefineState* st, const CellRec
     out[sv] = r;
 }
 
+// acquisition.py:179-189 over every (block, prn) row of a finished grid: first Doppler bin with the largest profile
+// maximum, its argmax and strength.  One thread per row (rows are D consecutive records).
+__global__ void k_best_bins(int n_rows, int D, int N, const CellRecord* rec, const double* doppler, BestRecord* out) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const CellRecord* r = rec + static_cast<size_t>(row) * D;
+    int best = 0;
+    float best_peak = r[0].peak;
+    for (int d = 1; d < D; ++d) {
+        const float p = r[d].peak;
+        if (p > best_peak) {  // strict: the first bin wins ties (max() over dict order, acquisition.py:180-182)
+            best = d;
+            best_peak = p;
+        }
+    }
+    const CellRecord w = r[best];
+    const double peak = static_cast<double>(w.peak);
+    BestRecord o;
+    o.doppler = doppler[best];
+    o.strength = peak / ((w.sum - w.count * peak) / (N - w.count));  // utils.py:111-116
+    o.peak = w.peak;
+    o.code_phase = w.argmax;
+    o.bin = best;
+    o.pad_ = 0;
+    out[row] = o;
+}
+cudaError_t launch_best_bins(int n_rows, int D, int N, const CellRecord* rec, const double* doppler, BestRecord* out,
+                             cudaStream_t s) {
+    k_best_bins<<<(n_rows + 127) / 128, 128, 0, s>>>(n_rows, D, N, rec, doppler, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_refine_init(int n_sv, RefineState* st, cudaStream_t s) {
     k_refine_init<<<(n_sv + 63) / 64, 64, 0, s>>>(n_sv, st);
     return cudaGetLastError();

@@ -61,6 +61,16 @@ struct RefineResult {  // 32 bytes, mirrored by gb200_acquisition_result
     int code_phase;
     int pad_;
 };
+struct BestRecord {  // 32 bytes, mirrored by gb200_best_record
+    double doppler;
+    double strength;
+    float peak;
+    int code_phase;
+    int bin;
+    int pad_;
+};
+cudaError_t launch_best_bins(int n_rows, int D, int N, const CellRecord* rec, const double* doppler, BestRecord* out,
+                             cudaStream_t s);
 cudaError_t launch_refine_plan(int n_sv, double spread, const RefineState* st, double* doppler, cudaStream_t s);
 cudaError_t launch_refine_select(int n_sv, int N, const CellRecord* rec, const double* doppler, RefineState* st, cudaStream_t s);
 cudaError_t launch_refine_coherent_plan(int n_sv, const RefineState* st, double* doppler, int* probe, cudaStream_t s);
@@ -79,6 +89,9 @@ struct TrackArgs {
     const float2* tw2;
     double fs, inv_fs;
     int N, s, n_ms, n_channels;
+    double t0_single;           // start time used when start_times is null (single-millisecond launches: no upload)
+    const int* channel_idx;     // optional [n_channels]: CTA b runs channel channel_idx[b] (records still go to out[b]); null = b
+    TrackState* shadow;         // optional [capacity]: every launched channel's state as it was BEFORE this launch (rollback)
 };
 
 // integrate_bits: one warp per tracking channel (bits.cu, bits_core.cuh).

@@ -56,15 +56,22 @@ __global__ void __launch_bounds__(kTrackThreads, 1) k_track_channels(const Track
     float2* coarse = el + 2;                                          // [16] carrier at samples 0, 256, ... (+ phase)
     uint64_t* mbar = reinterpret_cast<uint64_t*>(coarse + 16);
 
-    const int ch = blockIdx.x;
+    const int slot = blockIdx.x;                                     // where this CTA's records go
+    const int ch = a.channel_idx ? a.channel_idx[slot] : slot;       // which channel's state it advances
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     TrackState* gst = a.states + ch;
 
-    // ---- load the channel state, the twiddles and this PRN's replica spectrum ----
+    // ---- load the channel state (keeping a copy for a later rollback when asked to), the twiddles and this PRN's
+    //      replica spectrum ----
     {
         const int* src = reinterpret_cast<const int*>(gst);
         int* dst = reinterpret_cast<int*>(st);
-        for (int i = tid; i < static_cast<int>(sizeof(TrackState) / 4); i += kTrackThreads) dst[i] = src[i];
+        int* shd = a.shadow ? reinterpret_cast<int*>(a.shadow + ch) : nullptr;
+        for (int i = tid; i < static_cast<int>(sizeof(TrackState) / 4); i += kTrackThreads) {
+            const int v = src[i];
+            dst[i] = v;
+            if (shd) shd[i] = v;
+        }
     }
     if (tid == 0) mbar_init(mbar, 1);
     __syncthreads();
@@ -88,7 +95,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) k_track_channels(const Track
     const int r = warp >> 1, h = warp & 1;
     float2* tile = tiles + warp * kTileF2;
     const float2* ptile = tiles + (warp ^ 1) * kTileF2;
-    TrackMsRecord* out = a.out + static_cast<size_t>(ch) * a.n_ms;
+    TrackMsRecord* out = a.out + static_cast<size_t>(slot) * a.n_ms;
 
     for (int k = 0; k < a.n_ms; ++k) {
         if (k + 1 < a.n_ms) {
@@ -102,14 +109,14 @@ __global__ void __launch_bounds__(kTrackThreads, 1) k_track_channels(const Track
             if (tid == 0) {
                 TrackMsRecord rec = {};
                 rec.lost = 2;
-                rec.doppler = st->doppler;
-                rec.carrier_phase = st->carrier_phase;
+                rec.doppler = rec.doppler_hist = st->doppler;
+                rec.carrier_phase = rec.carrier_phase_hist = st->carrier_phase;
                 rec.code_phase = st->code_phase;
                 out[k] = rec;
             }
             continue;
         }
-        const double f = st->doppler, phi_cycles = st->carrier_phase * (1.0 / kTau), t0 = a.start_times[k];
+        const double f = st->doppler, phi_cycles = st->carrier_phase * (1.0 / kTau), t0 = a.start_times ? a.start_times[k] : a.t0_single;
         const int p = st->code_phase;
         const int pm = pymod_int(p, a.N);
         const int kE = pymod_int(p - 1, a.N), kL = pymod_int(p + 1, a.N);
@@ -177,7 +184,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) k_track_channels(const Track
                     sum += v;
                     if (n == kE) el[0] = make_float2(xr[jj], xi[jj]);
                     if (n == kL) el[1] = make_float2(xr[jj], xi[jj]);
-                    if (a.profiles) a.profiles[(static_cast<size_t>(ch) * a.n_ms + k) * a.N + kk] = v;
+                    if (a.profiles) a.profiles[(static_cast<size_t>(slot) * a.n_ms + k) * a.N + kk] = v;
                 }
             }
             const int bits = __float_as_int(mx);

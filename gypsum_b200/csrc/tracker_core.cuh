@@ -32,12 +32,13 @@ struct TrackState {
     double peak_re[kPeakRing], peak_im[kPeakRing];
 };
 
-// One millisecond of one channel, as handed back to the host (96 bytes).
+// One millisecond of one channel, as handed back to the host (112 bytes).
 struct TrackMsRecord {
-    double doppler, carrier_phase;  // after this millisecond's update (tracker.py:352-353 histories)
+    double doppler, carrier_phase;  // current_* after this millisecond, INCLUDING the 6-second adjustment of tracker.py:380-387
     double error;                   // I*Q Costas discriminator (tracker.py:249)
     double disc;                    // (|E|^2 - |L|^2)/2 (tracker.py:297)
     double phase_acc;               // self.phase after the update
+    double doppler_hist, carrier_phase_hist;  // what tracker.py:352-353 append to the histories: the loop state BEFORE that adjustment
     float peak_re, peak_im;         // coherent prompt peak (tracker.py:313)
     float strength;                 // tracker.py:311
     float early_re, early_im, late_re, late_im;
@@ -48,7 +49,7 @@ struct TrackMsRecord {
     int peak_offset;                // argmax of the rolled prompt profile (tracker.py:310)
     int pad_[2];
 };
-static_assert(sizeof(TrackMsRecord) == 96, "track record must stay 96 bytes");
+static_assert(sizeof(TrackMsRecord) == 112, "track record must stay 112 bytes");
 
 GB_HD GB_INLINE double pymod(double a, double m) {  // Python's float % for m > 0
     double r = fmod(a, m);
@@ -224,6 +225,8 @@ GB_HD inline void track_update(TrackState& st, float2 E, float2 L, float2 peak, 
     st.carrier_phase = pymod(st.carrier_phase, kTau);
     st.doppler += error * beta;
     track_push_error(st, error);
+    out.doppler_hist = st.doppler;  // tracker.py:352-353: appended to the histories before the check below
+    out.carrier_phase_hist = st.carrier_phase;
     // --- periodic constellation check, tracker.py:370-387 ---
     int lost = 0;
     if (start_time - st.last_circ_time >= 6.0) {

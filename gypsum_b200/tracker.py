@@ -1,9 +1,10 @@
 """Drop-in for reference gypsum/tracker.py: GpsSatelliteTracker, GpsSatelliteTrackingParameters and the
 pseudosymbol types, same names / fields / exception (tracker.py:33-110, :117-155, :206-389).
 
-`GpsSatelliteTracker.process_samples(chunk)` keeps the reference's one-millisecond-per-call contract (one GPU
-round trip per call).  `TrackerBank` is the throughput interface: many channels x many milliseconds in one
-persistent-kernel launch.  The correlators, loop filters, lock heuristics and the 6-second constellation check
+`GpsSatelliteTracker.process_samples(chunk)` keeps the reference's one-millisecond-per-call contract; the trackers of
+one engine share a channel pool, so a chunk handed to N trackers in turn costs one GPU round trip, not N
+(`_ChannelPool`).  `TrackerBank` is the throughput interface: many channels x many milliseconds in one persistent-kernel
+launch.  The correlators, loop filters, lock heuristics and the 6-second constellation check
 all run on the device (gypsum_b200/csrc/tracker.cu, tracker_core.cuh); this module only mirrors the host-visible
 state and histories the rest of gypsum reads.
 """
@@ -121,7 +122,7 @@ def _replica_index(ent, satellite, n: int) -> int:
 
 
 def _apply_record(params: GpsSatelliteTrackingParameters, rec, profile=None) -> None:
-    """What tracker.py:299-353 appends / assigns during one process_samples call."""
+    """What tracker.py:299-387 appends / assigns during one process_samples call."""
     peak = complex(float(rec["peak_re"]), float(rec["peak_im"]))
     params.current_prn_code_phase_shift = int(rec["code_phase"])
     params.discriminators.append(float(rec["disc"]))
@@ -130,12 +131,14 @@ def _apply_record(params: GpsSatelliteTrackingParameters, rec, profile=None) -> 
         params.non_coherent_correlation_profiles.append(profile)
     params.correlation_peaks_rolling_buffer.append(peak)
     params.correlation_peak_strengths_rolling_buffer.append(float(rec["strength"]))
-    params.current_carrier_wave_phase_shift = float(rec["carrier_phase"])
-    params.current_doppler_shift = float(rec["doppler"])
     params.carrier_wave_phase_errors.append(float(rec["error"]))
     params.correlation_peak_angles.append(float(np.angle(peak)))
-    params.doppler_shifts.append(params.current_doppler_shift)
-    params.carrier_wave_phases.append(params.current_carrier_wave_phase_shift)
+    # tracker.py:352-353 append the loop state to the histories BEFORE the 6-second constellation adjustment of :370-387;
+    # current_* end up with the adjusted values
+    params.doppler_shifts.append(float(rec["doppler_hist"]))
+    params.carrier_wave_phases.append(float(rec["carrier_phase_hist"]))
+    params.current_carrier_wave_phase_shift = float(rec["carrier_phase"])
+    params.current_doppler_shift = float(rec["doppler"])
     params._last_is_locked = bool(rec["locked"])
 
 
@@ -144,6 +147,96 @@ def _pseudosymbol(rec, start_time: float, end_time: float) -> EmittedPseudosymbo
     return EmittedPseudosymbol(
         start_of_pseudosymbol=start_time + delay, end_of_pseudosymbol=end_time + delay,
         pseudosymbol=NavigationBitPseudosymbol.from_val(int(rec["symbol"])), cursor_at_emit_time=0)
+
+
+def _chunk_key(chunk) -> tuple:
+    ring = getattr(chunk, "device_ring", None)
+    if ring is not None:
+        return ("ring", id(ring), int(chunk.ring_index))
+    return (id(chunk.samples), float(chunk.start_time))
+
+
+class _ChannelPool:
+    """Every GpsSatelliteTracker of one engine is a channel slot of ONE native pool (gb200_tracker_create_pool).
+
+    The receiver hands the same chunk to every tracked satellite in turn (receiver.py:103-106, :237-257).  When the first
+    tracker is asked about a chunk, all channels of the pool advance through it in one launch (one upload, one kernel, one
+    read-back instead of one of each per satellite); the others find their millisecond already computed.  The kernel keeps
+    each channel's previous state, so a channel that is then asked about a DIFFERENT chunk, or whose loop state the host
+    edited in between, takes the step back (gb200_tracker_undo_channel) and is recomputed -- results never depend on the
+    batching."""
+
+    CAPACITY = 64  # 32 GPS PRNs; room for re-acquisitions that overlap a dropped tracker's lifetime
+
+    def __init__(self, ent):
+        self.engine = ent["engine"]
+        self.native = _native.Tracker.pool(self.engine, self.CAPACITY)
+        self.free = list(range(self.CAPACITY - 1, -1, -1))
+        self.members: dict = {}   # channel -> weakref to its GpsSatelliteTracker
+        self.ahead: dict = {}     # channel -> (chunk key, record, profile or None): computed, not yet asked for
+        self.stopped: set = set()  # channels whose device state carries `lost` (cleared by the next set_state)
+        self.last: dict = {}      # channel -> key of the chunk it was last asked about
+
+    def join(self, tracker, prn_idx: int, doppler: float, carrier_phase: float, code_phase: int) -> int:
+        import weakref
+
+        if not self.free:
+            raise RuntimeError(f"more than {self.CAPACITY} live trackers on one engine")
+        ch = self.free.pop()
+        self.native.reset_channel(ch, prn_idx, doppler, carrier_phase, code_phase)
+        self.members[ch] = weakref.ref(tracker)
+        self.last.pop(ch, None)
+        return ch
+
+    def leave(self, ch: int) -> None:
+        if self.members.pop(ch, None) is not None:
+            self.ahead.pop(ch, None)
+            self.stopped.discard(ch)
+            self.free.append(ch)
+
+    def drop_ahead(self, ch: int) -> None:
+        """The channel was advanced through a chunk nobody asked it about: put its previous state back."""
+        if self.ahead.pop(ch, None) is not None:
+            self.native.undo_channel(ch)
+
+    def _load(self, chunk, key) -> None:
+        ring = getattr(chunk, "device_ring", None)
+        if ring is not None and ring.holds_newest(chunk):
+            ring.native.bind_newest(1)  # the millisecond is already on the device (one upload for detector and trackers)
+        elif self.engine.iq_tag != key:
+            self.engine.upload_iq(chunk.samples, tag=key)
+
+    def step(self, ch: int, chunk, want_profile: bool):
+        key = _chunk_key(chunk)
+        got = self.ahead.pop(ch, None)
+        self.last[ch] = key
+        if got is not None:
+            if got[0] == key and (got[2] is not None or not want_profile):
+                return got[1], got[2]
+            self.native.undo_channel(ch)
+        # every other channel that has not seen this chunk and has nothing computed ahead will be asked about it next
+        sel, profs = [ch], want_profile
+        for c, ref in list(self.members.items()):
+            trk = ref()
+            if trk is None:
+                self.leave(c)
+            elif (c != ch and c not in self.ahead and c not in self.stopped and self.last.get(c) != key
+                  and not trk._host_edited()):
+                sel.append(c)
+                profs = profs or trk.keep_correlation_profiles
+        self._load(chunk, key)
+        got = self.native.process_channels(sel, 1, [float(chunk.start_time)], want_profiles=profs, keep_undo=True)
+        recs, prof = got if profs else (got, None)
+        for i, c in enumerate(sel[1:], start=1):
+            self.ahead[c] = (key, recs[i, 0].copy(), None if prof is None else prof[i, 0])
+        return recs[0, 0].copy(), (None if prof is None else prof[0, 0])
+
+
+def _pool_of(ent) -> _ChannelPool:
+    pool = ent.get("tracker_pool")
+    if pool is None:
+        pool = ent["tracker_pool"] = _ChannelPool(ent)
+    return pool
 
 
 class GpsSatelliteTracker:
@@ -158,39 +251,57 @@ class GpsSatelliteTracker:
         self._ent = POOL.get(fs, n)
         self._eng = self._ent["engine"]
         idx = _replica_index(self._ent, tracking_params.satellite, n)
-        self._native = _native.Tracker(self._eng, [idx], [tracking_params.current_doppler_shift],
-                                       [tracking_params.current_carrier_wave_phase_shift],
-                                       [tracking_params.current_prn_code_phase_shift])
-        self._device_view = (float(tracking_params.current_doppler_shift),
-                             float(tracking_params.current_carrier_wave_phase_shift),
-                             int(tracking_params.current_prn_code_phase_shift), float(self.phase))
+        self._pool = _pool_of(self._ent)
+        self._channel = self._pool.join(self, idx, tracking_params.current_doppler_shift,
+                                        tracking_params.current_carrier_wave_phase_shift,
+                                        tracking_params.current_prn_code_phase_shift)
+        self._device_view = self._host_view()
+
+    def close(self) -> None:
+        if getattr(self, "_channel", None) is not None:
+            self._pool.leave(self._channel)
+            self._channel = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _host_view(self) -> tuple:
+        p = self.tracking_params
+        return (float(p.current_doppler_shift), float(p.current_carrier_wave_phase_shift),
+                int(p.current_prn_code_phase_shift), float(self.phase))
+
+    def _host_edited(self) -> bool:
+        return self._host_view() != self._device_view
 
     def _push_host_edits(self) -> None:
-        """If a caller changed tracking_params.current_* (or self.phase) since the last call, the device follows."""
-        p = self.tracking_params
-        now = (float(p.current_doppler_shift), float(p.current_carrier_wave_phase_shift),
-               int(p.current_prn_code_phase_shift), float(self.phase))
-        if now != self._device_view:
-            self._native.set_state(0, now[0], now[1], now[3], now[2])
+        """If a caller changed tracking_params.current_* (or self.phase) since the last call, the device follows.  A
+        channel that raised LostSatelliteLockError keeps working when asked again, like the reference object: its device
+        flag is cleared by the same call."""
+        now = self._host_view()
+        stopped = self._channel in self._pool.stopped
+        if now != self._device_view or stopped:
+            self._pool.drop_ahead(self._channel)  # anything computed ahead used the old state
+            self._pool.native.set_state(self._channel, now[0], now[1], now[3], now[2])
+            self._pool.stopped.discard(self._channel)
             self._device_view = now
 
     def process_samples(self, receiver_samples_chunk) -> EmittedPseudosymbol:
         """tracker.py:331-389."""
         self._push_host_edits()
-        samples = receiver_samples_chunk.samples
-        key = (id(samples), float(receiver_samples_chunk.start_time))
-        if self._eng.iq_tag != key:  # several trackers usually share one chunk: upload it once.  The tag lives in the
-            self._eng.upload_iq(samples, tag=key)  # engine wrapper and every other upload / bind clears it
-        got = self._native.process(1, [receiver_samples_chunk.start_time], want_profiles=self.keep_correlation_profiles)
-        rec, prof = (got[0][0, 0], got[1][0, 0]) if self.keep_correlation_profiles else (got[0, 0], None)
+        rec, prof = self._pool.step(self._channel, receiver_samples_chunk, self.keep_correlation_profiles)
+        if int(rec["lost"]) >= 2:  # cannot happen through this class (the flag is cleared above); never hand out a placeholder
+            raise LostSatelliteLockError()
         if int(rec["symbol"]) == 0:
             raise KeyError(0)  # tracker.py:317: NavigationBitPseudosymbol.from_val has no entry for 0
-        _apply_record(self.tracking_params, rec, None if prof is None else prof.astype(np.float64))
+        keep = self.keep_correlation_profiles and prof is not None
+        _apply_record(self.tracking_params, rec, prof.astype(np.float64) if keep else None)
         self.phase = float(rec["phase_acc"])
-        p = self.tracking_params
-        self._device_view = (float(p.current_doppler_shift), float(p.current_carrier_wave_phase_shift),
-                             int(p.current_prn_code_phase_shift), float(self.phase))
+        self._device_view = self._host_view()
         if int(rec["lost"]):
+            self._pool.stopped.add(self._channel)
             raise LostSatelliteLockError()  # tracker.py:378
         return _pseudosymbol(rec, receiver_samples_chunk.start_time, receiver_samples_chunk.end_time)
 
@@ -215,6 +326,11 @@ class TrackerBank:
         x = np.ascontiguousarray(samples, dtype=np.complex64)
         n_ms = x.size // self.samples_per_ms
         self.engine.upload_iq(x[: n_ms * self.samples_per_ms])
+        return self.native.process(n_ms, start_times, want_profiles)
+
+    def process_ring(self, ring, n_ms: int, start_times, want_profiles: bool = False):
+        """The newest n_ms milliseconds of a DeviceSampleRing, in place (no upload)."""
+        ring.native.bind_newest(n_ms)
         return self.native.process(n_ms, start_times, want_profiles)
 
     def integrate_bits(self, start_times, end_times) -> list:

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define GB200_ABI_VERSION 1
+#define GB200_ABI_VERSION 2
 
 #define GB200_OK 0
 #define GB200_EINVAL 1  /* bad argument            -> ValueError  (utils.py:106) */
@@ -67,7 +67,22 @@ int gb200_set_replicas(gb200_engine* e, const uint8_t* chips, int n_prn);
 /* receiver.py:219 antenna_data: complex64[n_samples] (interleaved float32 I,Q -- the on-disk format of
  * antenna_sample_provider.py:112-119).  upload copies from the host; bind uses a device buffer in place.    */
 int gb200_upload_iq(gb200_engine* e, const float* iq_host, int64_t n_samples);
+/* iq_device must be 16-byte aligned (the fused and tracking kernels stage it with bulk / cp.async copies). */
 int gb200_bind_iq_device(gb200_engine* e, const void* iq_device, int64_t n_samples);
+
+/* receiver.py:68,100,219 rolling_samples_buffer (deque(maxlen=ACQUISITION_INTEGRATION_PERIOD_MS)) on the device: every
+ * new millisecond of antenna_sample_provider.py:94-124 is uploaded ONCE (one 8*N-byte copy) and both the detector's
+ * 10-ms window and every tracking channel read it in place.  The newest n_ms <= capacity_ms milliseconds are always
+ * contiguous in device memory (each millisecond is stored twice, capacity_ms apart).                                  */
+typedef struct gb200_ring gb200_ring;
+int gb200_ring_create(gb200_engine* e, int capacity_ms, gb200_ring** out);
+int gb200_ring_destroy(gb200_ring* r);
+/* Append n_ms whole milliseconds (complex64[n_ms * N]) from host memory. */
+int gb200_ring_append(gb200_ring* r, const float* iq_host, int n_ms);
+/* The engine's IQ binding := the newest n_ms milliseconds (zero copy); what gb200_detect / gb200_acquire_* /
+ * gb200_tracker_process* then read.  n_ms <= min(capacity_ms, milliseconds appended so far).                          */
+int gb200_ring_bind_newest(gb200_ring* r, int n_ms);
+int gb200_ring_appended(const gb200_ring* r, int64_t* total_ms);
 
 /* Benchmark-shaped search grid: the loaded IQ holds n_blocks independent blocks of
  * ms_per_block milliseconds; every (block, prn_idx[a], doppler_hz[b]) cell is one
@@ -77,6 +92,28 @@ int gb200_acquire_grid(gb200_engine* e, int n_blocks, int ms_per_block, const in
                        const double* doppler_hz, int n_doppler, int integration_type, gb200_cell_record* out_host);
 int gb200_acquire_grid_device(gb200_engine* e, int n_blocks, int ms_per_block, const int32_t* prn_idx, int n_prn,
                               const double* doppler_hz, int n_doppler, int integration_type, void* out_device);
+/* The same grid host to host in ONE call for latency-bound callers (receiver.py:219-224 hands over one window per
+ * scan): copy-in, both kernels and copy-out are replayed as one CUDA graph per grid shape, one host synchronisation.
+ * iq_host: complex64[n_blocks * ms_per_block * N].                                                                    */
+int gb200_acquire_grid_host(gb200_engine* e, const float* iq_host, int n_blocks, int ms_per_block, const int32_t* prn_idx,
+                            int n_prn, const double* doppler_hz, int n_doppler, int integration_type,
+                            gb200_cell_record* out_host);
+
+/* acquisition.py:179-189 applied to every (block, prn) row of a grid on the device: the first Doppler bin with the
+ * largest profile maximum, its code phase and strength -- 32 bytes per (block, prn) instead of 32 bytes per cell
+ * (what a multi-GPU gather has to move).  out[(block * n_prn + a)].                                    */
+typedef struct gb200_best_record {
+    double doppler_hz;  /* BestNonCoherentCorrelationProfile.doppler_shift                  (acquisition.py:186) */
+    double strength;    /* .correlation_strength                                            (acquisition.py:189) */
+    float peak;         /* np.max of the winning bin's profile                                                    */
+    int32_t code_phase; /* .sample_offset_of_correlation_peak                               (acquisition.py:184) */
+    int32_t bin;        /* index of the winning bin in doppler_hz                                                */
+    int32_t reserved;
+} gb200_best_record;
+int gb200_acquire_grid_best(gb200_engine* e, int n_blocks, int ms_per_block, const int32_t* prn_idx, int n_prn,
+                            const double* doppler_hz, int n_doppler, int integration_type, gb200_best_record* out_host);
+int gb200_acquire_grid_best_device(gb200_engine* e, int n_blocks, int ms_per_block, const int32_t* prn_idx, int n_prn,
+                                   const double* doppler_hz, int n_doppler, int integration_type, void* out_device);
 
 /* acquisition.py:154-190 get_best_doppler_shift_estimation / :122-136: an arbitrary list of (prn, Doppler)
  * cells over the first n_ms milliseconds of the loaded IQ.  probe_idx (may be NULL) gives, per cell, the
@@ -110,14 +147,16 @@ int gb200_correlation_profile(gb200_engine* e, int prn_idx, double doppler_hz, i
  * --------------------------------------------------------------------------------------------------------- */
 typedef struct gb200_tracker gb200_tracker;
 
-/* One millisecond of one channel (96 bytes): what GpsSatelliteTracker.process_samples (tracker.py:331-389)
+/* One millisecond of one channel (112 bytes): what GpsSatelliteTracker.process_samples (tracker.py:331-389)
  * leaves in tracking_params' histories plus the emitted pseudosymbol.                                        */
 typedef struct gb200_track_record {
-    double doppler;        /* current_doppler_shift after this ms            (tracker.py:260, :352)          */
-    double carrier_phase;  /* current_carrier_wave_phase_shift after this ms (tracker.py:258-259, :353)       */
+    double doppler;        /* current_doppler_shift when process_samples returns (tracker.py:260, :385)      */
+    double carrier_phase;  /* current_carrier_wave_phase_shift when it returns   (tracker.py:258-259, :386)   */
     double error;          /* Costas discriminator I*Q                       (tracker.py:249, :261)           */
     double disc;           /* (|E|^2 - |L|^2) / 2                            (tracker.py:297, :300)           */
     double phase_acc;      /* self.phase after the update                    (tracker.py:298-303)             */
+    double doppler_hist;       /* what :352 appends to doppler_shifts: the value BEFORE the 6-s adjustment of :380-387 */
+    double carrier_phase_hist; /* what :353 appends to carrier_wave_phases, likewise                          */
     float peak_re, peak_im; /* coherent prompt correlation peak              (tracker.py:313, :346)           */
     float strength;        /* get_normalized_correlation_peak_strength       (tracker.py:311, :347)           */
     float early_re, early_im, late_re, late_im; /* np.correlate taps         (tracker.py:293-295)             */
@@ -144,8 +183,25 @@ int gb200_tracker_process_device(gb200_tracker* t, int n_ms, const double* start
 /* Read / overwrite the loop state of one channel (tracking_params.current_* and tracker.phase). */
 int gb200_tracker_get_state(gb200_tracker* t, int channel, double* doppler_hz, double* carrier_phase, double* phase_acc,
                             int32_t* code_phase, int32_t* lost);
+/* set_state also clears the channel's `lost` flag (the reference tracker object keeps working after it raised). */
 int gb200_tracker_set_state(gb200_tracker* t, int channel, double doppler_hz, double carrier_phase, double phase_acc,
                             int32_t code_phase);
+
+/* A pool of channel slots for callers that create and drop trackers one at a time (receiver.py:226-267: one
+ * GpsSatelliteTracker per acquired satellite, dropped on LostSatelliteLockError).  gb200_tracker_create_pool makes
+ * `capacity` idle slots; gb200_tracker_reset_channel seeds one like satellite_signal_processing_pipeline.py:56-63 does
+ * (fresh histories, lost = 0).  gb200_tracker_process_channels is gb200_tracker_process for a chosen subset in ONE
+ * launch: out_host[i * n_ms + ms] belongs to channels[i].  With keep_undo != 0 every launched channel's state before
+ * the call is kept, and gb200_tracker_undo_channel puts it back -- used by the drop-in GpsSatelliteTracker objects,
+ * which advance all channels that share a chunk with one launch when the first of them is asked
+ * (receiver.py:103-106 loops the same chunk over every pipeline) and take the step back for a channel that turns
+ * out not to be asked.                                                                                                */
+int gb200_tracker_create_pool(gb200_engine* e, int capacity, gb200_tracker** out);
+int gb200_tracker_reset_channel(gb200_tracker* t, int channel, int32_t prn_idx, double doppler_hz, double carrier_phase,
+                                int32_t code_phase);
+int gb200_tracker_process_channels(gb200_tracker* t, int n_sel, const int32_t* channels, int n_ms, const double* start_times,
+                                   int keep_undo, gb200_track_record* out_host, float* profiles_host);
+int gb200_tracker_undo_channel(gb200_tracker* t, int channel);
 
 /* A pipelined stream of equally shaped grid batches -- the receiver's steady state (receiver.py:85-146 hands over one
  * block after another): `submit` copies a batch of n_blocks*M*N complex64 samples from host memory, runs the grid of

@@ -117,26 +117,35 @@ class Acquisition:
     strength: float
 
 
-def best_bin(center: float, spread: float, data: np.ndarray, fs: int, n: int, prn: np.ndarray) -> BestBin:
+def best_bin(center: float, spread: float, data: np.ndarray, fs: int, n: int, prn: np.ndarray, trace=None) -> BestBin:
     """acquisition.py:154-190: non-coherent profile per bin; the winner is the FIRST bin with the largest
-    profile maximum (python max over dict insertion order); argmax = first index; strength per utils.py:111."""
+    profile maximum (python max over dict insertion order); argmax = first index; strength per utils.py:111.
+    trace (tests only): receives this pass's (bins, per-bin profile maxima, per-bin top-2 gap of the profile)."""
     best = None
-    for f in doppler_bins(center, spread):
+    bins, peaks, gaps = doppler_bins(center, spread), [], []
+    for f in bins:
         prof = integrate(NON_COHERENT, data, fs, n, f, prn)
+        if trace is not None:
+            top2 = np.partition(prof, -2)[-2:]
+            peaks.append(float(top2[1]))
+            gaps.append(float(top2[1] - top2[0]))
         if best is None or np.max(prof) > np.max(best[1]):
             best = (f, prof)
     f, prof = best
-    return BestBin(f, prof, int(np.argmax(prof)), float(peak_strength(prof)))
+    out = BestBin(f, prof, int(np.argmax(prof)), float(peak_strength(prof)))
+    if trace is not None:
+        trace.append(dict(bins=bins, peaks=peaks, gaps=gaps, chosen=f, strength=out.strength))
+    return out
 
 
-def acquire_sv(sv: int, data: np.ndarray, fs: int, n: int) -> Acquisition:
+def acquire_sv(sv: int, data: np.ndarray, fs: int, n: int, trace=None) -> Acquisition:
     """acquisition.py:70-152: spread 7000 halved while >= 10 (10 passes); each pass re-centres on that pass's
     best bin; the kept result is the pass with the strictly greatest strength; then one coherent integration
     at the kept Doppler gives the carrier phase at the kept (non-coherent) peak index."""
     prn = replica(sv, n)
     center, spread, kept = 0.0, 7000.0, None
     while spread >= 10:
-        b = best_bin(center, spread, data, fs, n, prn)
+        b = best_bin(center, spread, data, fs, n, prn, trace)
         spread /= 2
         center = b.doppler
         if kept is None or b.strength > kept.strength:
@@ -168,6 +177,22 @@ def grid_cells(data: np.ndarray, fs: int, n: int, svs: list[int], dopplers: list
             total[a, b] = mag.sum()
             count[a, b] = int(np.count_nonzero(mag == mag.max()))
     return peak, arg, total, count
+
+
+def search_is_ambiguous(trace, rel: float) -> bool:
+    """Tests only: True when a float32 implementation may legitimately take a different branch of acquire_sv than the
+    float64 one -- in some pass two bins' profile maxima, or the winning bin's two largest profile values, or two passes'
+    strengths around the kept one, lie within `rel` (relative) of each other."""
+    strengths = [p["strength"] for p in trace]
+    for p in trace:
+        pk = np.sort(np.asarray(p["peaks"]))
+        if len(pk) > 1 and pk[-1] - pk[-2] <= rel * pk[-1]:
+            return True
+        w = p["bins"].index(p["chosen"])
+        if p["gaps"][w] <= rel * p["peaks"][w]:
+            return True
+    st = np.sort(np.asarray(strengths))
+    return len(st) > 1 and st[-1] - st[-2] <= rel * st[-1]
 
 
 def strength_from_record(peak: float, total: float, count: int, n: int) -> float:

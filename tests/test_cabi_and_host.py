@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol(native_lib):
     assert declared == set(_native.SYMBOLS), declared ^ set(_native.SYMBOLS)
     for name in declared:
         assert getattr(native_lib, name) is not None
-    assert native_lib.gb200_abi_version() == 1
+    assert native_lib.gb200_abi_version() == 2
     assert _native.RECORD_DTYPE.itemsize == 32
     assert [_native.RECORD_DTYPE.fields[k][1] for k in ("peak", "argmax", "sum", "count", "probe_re", "probe_im")] == [
         0, 4, 8, 16, 20, 24]
@@ -113,5 +113,5 @@ int main(void) {
                     f"-Wl,-rpath,{os.path.dirname(_native.LIB_PATH)}"], check=True, capture_output=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines()
     fields = [int(v) for v in out[0].split()]
-    assert fields[1:5] == [32, 96, 32, 32]
+    assert fields[0] == 2 and fields[1:5] == [32, 112, 32, 32]
     assert fields[5] == 0 or "no usable CUDA device" in out[1]

@@ -43,6 +43,23 @@ class _OracleEngine:
             peak, arg, total, count = o.grid_cells(self.iq[b * ms * n:(b + 1) * ms * n], n * 1000, n, [int(p) + 1 for p in prn], list(dop))
             rec[b]["peak"], rec[b]["argmax"], rec[b]["sum"], rec[b]["count"] = peak, arg, total, count
         ctypes.memmove(out_ptr, rec.ctypes.data, rec.nbytes)
+        return rec
+
+    def acquire_grid_best_device(self, n_blocks, ms, prn, dop, kind, out_ptr):
+        """acquisition.py:179-189 per (block, prn) row of the same grid."""
+        import ctypes
+        from gypsum_b200._native import BEST_DTYPE
+
+        scratch = np.zeros(n_blocks * prn.size * dop.size * 32, dtype=np.uint8)
+        rec = self.acquire_grid_device(n_blocks, ms, prn, dop, kind, scratch.ctypes.data)
+        best = np.zeros((n_blocks, prn.size), dtype=BEST_DTYPE)
+        n = self.samples_per_ms
+        for b in range(n_blocks):
+            for a in range(prn.size):
+                k = int(np.argmax(rec[b, a]["peak"]))
+                r = rec[b, a, k]
+                best[b, a] = (dop[k], r["peak"] / ((r["sum"] - r["count"] * r["peak"]) / (n - r["count"])), r["peak"], r["argmax"], k, 0)
+        ctypes.memmove(out_ptr, best.ctypes.data, best.nbytes)
 
 
 def _worker(rank, world, port, q):
@@ -71,7 +88,9 @@ def _block_worker(rank, world, port, q):
     x = o.synth_iq(6, 2046, 5, 2046000, [(9, -500.0, 1234, 0.0, 0.4)]) if rank == 0 else None
     search = ShardedBlockSearch(_OracleEngine(), "cpu")
     full = search.acquire_blocks(x, 5, 1, np.array([8, 0]), [-500.0, 0.0], 2)
-    q.put((rank, None if full is None else (full["peak"].copy(), full["argmax"].copy())))
+    moved = dict(search.last_bytes)
+    best = search.acquire_blocks(x, 5, 1, np.array([8, 0]), [-500.0, 0.0], 2, reduce="best")
+    q.put((rank, None if full is None else (full["peak"].copy(), full["argmax"].copy(), best.copy(), moved, dict(search.last_bytes))))
     dist.destroy_process_group()
 
 
@@ -94,12 +113,19 @@ def test_sharded_block_search_scatter_and_gather(world):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(got[r] is None for r in range(1, world))
-    peak, arg = got[0]
+    peak, arg, best, moved, moved_best = got[0]
     x = o.synth_iq(6, 2046, 5, 2046000, [(9, -500.0, 1234, 0.0, 0.4)])
     for b in range(5):
         pk, ag, _, _ = o.grid_cells(x[b * 2046:(b + 1) * 2046], 2046000, 2046, [9, 1], [-500.0, 0.0])
         assert np.allclose(peak[b], pk, rtol=1e-6) and np.array_equal(arg[b], ag)
         assert arg[b, 0, 0] == 1234
+        # reduce="best": acquisition.py:179-189 of each (block, prn) row -- SV9 is found in bin 0 at code phase 1234
+        assert (best[b, 0]["bin"], best[b, 0]["doppler"], best[b, 0]["code_phase"]) == (0, -500.0, 1234)
+        for a in range(2):
+            assert best[b, a]["bin"] == int(np.argmax(pk[a])) and np.isclose(best[b, a]["peak"], pk[a].max(), rtol=1e-6)
+    most = -(-5 // world)
+    assert moved["scatter"] == (world - 1) * most * 2046 * 8 and moved["gather"] == (world - 1) * most * 2 * 2 * 32
+    assert moved_best["gather"] == (world - 1) * most * 2 * 32  # one 32-byte record per (block, prn) instead of per cell
 
 
 @pytest.mark.parametrize("world", [2, 3])

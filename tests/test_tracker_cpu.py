@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 N, FS = 2046, 2046000
 TRACK_REC = np.dtype([("doppler", "<f8"), ("carrier_phase", "<f8"), ("error", "<f8"), ("disc", "<f8"), ("phase_acc", "<f8"),
-                      ("peak_re", "<f4"), ("peak_im", "<f4"), ("strength", "<f4"), ("early_re", "<f4"), ("early_im", "<f4"),
+                      ("doppler_hist", "<f8"), ("carrier_phase_hist", "<f8"), ("peak_re", "<f4"), ("peak_im", "<f4"), ("strength", "<f4"), ("early_re", "<f4"), ("early_im", "<f4"),
                       ("late_re", "<f4"), ("late_im", "<f4"), ("code_phase", "<i4"), ("symbol", "<i4"), ("locked", "<i4"),
                       ("lost", "<i4"), ("peak_offset", "<i4"), ("pad0", "<i4"), ("pad1", "<i4")])
 
@@ -50,7 +50,7 @@ def test_oracle_tracker_bit_exact_with_reference(name, limit):
 def test_scalar_loop_teacher_forced(emu_lib, name):
     """track_update (DLL, PLL, is_locked with sliding sums, 6-s constellation check) fed the oracle's per-ms E/L/peak
     reproduces the reference's Doppler / phase / code-phase / lock-loss trajectory."""
-    assert TRACK_REC.itemsize == 96
+    assert TRACK_REC.itemsize == 112
     z, ch, x = load_case(name)
     init = z["init"]
     tr = t.TrackerOracle(ch[0], init[0], init[1], int(init[2]), FS, N)

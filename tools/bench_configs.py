@@ -145,7 +145,7 @@ def tracker_case(n_ch, n_ms):
     times = np.array([round(k * n / fs, 6) for k in range(n_ms)])
     xd = torch.from_numpy(x).cuda()
     eng.bind_iq_device(xd.data_ptr(), x.size)
-    out = torch.empty(n_ch * n_ms * 96, dtype=torch.uint8, device="cuda")
+    out = torch.empty(n_ch * n_ms * _native.TRACK_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     trk.process_device(n_ms, times, out.data_ptr())
