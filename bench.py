@@ -159,28 +159,62 @@ def _cpu_track_worker(args):
     return sym
 
 
-class CpuPool:
-    """A fork pool with one process per host core, created BEFORE CUDA is initialised in this process."""
+def usable_cores() -> int:
+    """Host threads this process may actually run on: the affinity mask, capped by a cgroup CPU quota when there is one."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return n
 
-    def __init__(self):
+
+class CpuPool:
+    """Fork pools created BEFORE CUDA is initialised in this process.  The box reports more hardware threads than the
+    numpy path can use (SMT siblings share one FFT unit; a container quota may sit below the thread count), so the pool
+    size is CALIBRATED: the same two-block grid is timed at several process counts and the fastest one is kept -- the CPU
+    leg is given every host thread that helps it."""
+
+    def __init__(self, calibrate: bool = True):
         import multiprocessing as mp
 
-        self.cores = os.cpu_count() or 1
-        self.pool = mp.get_context("fork").Pool(self.cores)
-        self.pool.map(_warm, range(self.cores))
+        self.avail = usable_cores()
+        cands = sorted({c for c in (self.avail, self.avail // 2, self.avail // 4, 32, 16) if 1 <= c <= self.avail})
+        self.calibration = {}
+        best = None
+        blocks = noise_blocks(2, N, 7)
+        for c in (cands if calibrate else [self.avail]):
+            pool = mp.get_context("fork").Pool(c)
+            pool.map(_warm, range(c))
+            self.cores, self.pool = c, pool
+            sec = min(self.grid(blocks, FS, N, DOPPLERS)[1] for _ in range(2)) if calibrate else 0.0
+            self.calibration[c] = sec
+            if best is None or sec < best[0]:
+                if best is not None:
+                    best[2].terminate()
+                best = (sec, c, pool)
+            else:
+                pool.terminate()
+        _, self.cores, self.pool = best
 
     def grid(self, blocks: np.ndarray, fs: int, n: int, dop: np.ndarray):
         """Full 32 x D grid of every block in `blocks` [nb, M*n].  Returns (records [nb, 32, D, 4], seconds)."""
         nb, nd = blocks.shape[0], len(dop)
         cells = [(b, sv, d) for b in range(nb) for sv in range(1, N_PRN + 1) for d in range(nd)]
-        parts = [cells[i::self.cores] for i in range(self.cores)]  # interleaved: every process gets every PRN's share
+        # contiguous shares: a process sees few distinct (block, PRN) pairs, so its replica spectra stay in cache
+        bounds = [len(cells) * i // self.cores for i in range(self.cores + 1)]
+        parts = [cells[bounds[i]:bounds[i + 1]] for i in range(self.cores)]
         t0 = time.perf_counter()
-        res = self.pool.map(_cpu_cells_worker, [(blocks, fs, n, dop, p) for p in parts if p])
+        res = self.pool.map(_cpu_cells_worker, [(blocks, fs, n, dop, p) for p in parts if p], chunksize=1)
         sec = time.perf_counter() - t0
-        flat = np.zeros((len(cells), 4))
-        for i, r in enumerate(res):
-            flat[i::self.cores] = r
+        flat = np.concatenate(res, axis=0)
         return flat.reshape(nb, N_PRN, nd, 4), sec
+
+    def describe(self) -> str:
+        cal = ", ".join(f"{c}: {1e3 * s:.0f} ms" for c, s in sorted(self.calibration.items()))
+        return f"{self.cores} processes (fastest of the calibrated counts; two-block grid: {cal}; {self.avail} host threads usable)"
 
     def close(self):
         self.pool.terminate()
@@ -233,7 +267,7 @@ def run_reference(args, rank: int, world: int) -> None:
         "config": {"workload": WORKLOAD, "blocks_per_step": nb,
                    "sample": f"each step = the full 32x41 grid over {nb} 1-ms blocks (bounded sample of the GPU arm's step)"},
         "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": pool.cores, "kind": "port",
-                         "sample": f"{args.steps} steps x {nb} blocks x 1312 cells, cells interleaved over {pool.cores} processes"},
+                         "sample": f"{args.steps} steps x {nb} blocks x 1312 cells over {pool.describe()}"},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t_start,
     }
@@ -517,7 +551,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
                          "note": "algorithmic bytes are on-chip reuse traffic (each IQ byte feeds 1312 cells); DRAM traffic is near the compulsory minimum, the kernel is FP32-issue / shared-memory bound"},
             "cpu_baseline": {"value": cpu_sps / 1e6, "unit": "Msamples/s", "cores": cpu.cores, "kind": "port",
                              "single_thread_value": single_sps / 1e6,
-                             "sample": f"{args.cpu_blocks} of the GPU arm's 1-ms blocks x full 32x41 grid, median of 3, cells interleaved over {cpu.cores} processes"},
+                             "sample": f"{args.cpu_blocks} of the GPU arm's 1-ms blocks x full 32x41 grid, median of 3, cells over {cpu.describe()}"},
         }
     eng.close()
     del ring_dev, rec_dev
@@ -556,34 +590,37 @@ def multi_gpu_e2e(g, eng, args, prn, dop) -> dict:
         host = torch.from_numpy(make_ring(total_blocks, seed=77)).pin_memory().numpy().reshape(-1)
     search = ShardedBlockSearch(eng, torch.device("cuda", g.local_rank))
     out = {}
-    for mode in (None, "best"):
+    for key, mode in (("per_cell", None), ("best_bin", "best")):
         res = [None]
 
         def step(k: int) -> None:
-            res[0] = search.acquire_blocks(host, total_blocks, N_MS, prn, dop, _native.NON_COHERENT, reduce=mode)
+            res[0] = search.acquire_blocks(host, total_blocks, N_MS, prn, dop, _native.NON_COHERENT, reduce=mode, copy=False)
 
         step(0)
         steps = max(3, min(args.steps, 10))
-        sec = g.wall(step, steps, first=1)
+        sec = g.wall(step, steps, first=1) / steps
         if g.rank == 0:
             r = res[0]
             if mode is None:
                 assert r.shape == (total_blocks, N_PRN, len(dop))
-                assert int(r["argmax"][total_blocks - 1, 24, int(np.argmax(r["peak"][total_blocks - 1, 24]))]) == 777
+                for b in (0, total_blocks // 2, total_blocks - 1):
+                    assert int(r["argmax"][b, 24, int(np.argmax(r["peak"][b, 24]))]) == 777
             else:
                 assert (r["doppler"][total_blocks - 1, 24], r["code_phase"][total_blocks - 1, 24]) == (1500.0, 777)
-        key = "per_cell" if mode is None else "best_bin"
         out[key] = {"value": total_blocks * N / sec / 1e6, "seconds_per_step": sec, "steps": steps, **search.last_bytes}
     pc = out["per_cell"]
     return {"value": pc["value"], "unit": "Msamples/s", "h2d_bytes_per_step": pc["h2d"], "d2h_bytes_per_step": pc["d2h"],
             "nccl_scatter_bytes_per_step": pc["scatter"], "nccl_gather_bytes_per_step": pc["gather"],
-            "blocks_per_step": total_blocks,
+            "blocks_per_step": total_blocks, "seconds_per_step": pc["seconds_per_step"],
             "api": "ShardedBlockSearch.acquire_blocks: rank-0 pinned host IQ -> H2D -> NCCL scatter -> grid on every rank -> NCCL gather -> D2H -> rank-0 host records",
-            "with_on_device_best_bin_reduction": {"value": out["best_bin"]["value"], "d2h_bytes_per_step": out["best_bin"]["d2h"],
+            "with_on_device_best_bin_reduction": {"value": out["best_bin"]["value"], "seconds_per_step": out["best_bin"]["seconds_per_step"],
+                                                  "d2h_bytes_per_step": out["best_bin"]["d2h"],
                                                   "nccl_gather_bytes_per_step": out["best_bin"]["gather"],
                                                   "note": "acquisition.py:179-189 per (block, PRN) row on the device: 32 B per row instead of 32 B per cell"},
-            "limiter": "rank 0's PCIe link: every rank's per-cell records (42 KB per block) funnel through one device->host copy; "
-                       "the best-bin reduction removes 40/41 of it"}
+            "limiter": "the return path is serial behind the kernels: NCCL gather of every rank's per-cell records (42 KB per block) into rank 0, "
+                       "then ONE device->host copy over rank 0's PCIe link; overlapping the gather with the kernels was measured and is slower "
+                       "(profiles/ablation_r2.md: NCCL's kernels cannot co-reside with the persistent full-shared-memory correlate CTAs); "
+                       "the best-bin reduction removes 40/41 of the bytes"}
 
 
 def secondary_rooflines(traffic, corr_ms, call_ms, blocks, n_cells, clocks):
@@ -742,26 +779,28 @@ def bench_config5(g, cpu, peak_gbs, sampler, args) -> dict:
         search = ShardedBlockSearch(eng, torch.device("cuda", g.local_rank))
         flat = host.numpy().reshape(-1) if g.rank == 0 else None
         out = {}
-        for mode in (None, "best"):
+        for key, mode in (("per_cell", None), ("best_bin", "best")):
             got = [None]
 
             def job(k):
-                got[0] = search.acquire_blocks(flat, nb, 1, prn, dop, _native.NON_COHERENT, reduce=mode)
+                got[0] = search.acquire_blocks(flat, nb, 1, prn, dop, _native.NON_COHERENT, reduce=mode, copy=False)
 
             job(0)
-            sec = g.wall(job, 2, first=1) / 2
+            sec = g.wall(job, 3, first=1) / 3
             if g.rank == 0:
                 r = got[0]
                 if mode is None:
-                    assert int(r["argmax"][nb - 1, 24, int(np.argmax(r["peak"][nb - 1, 24]))]) == 16367
+                    for b in (0, nb // 2, nb - 1):
+                        assert int(r["argmax"][b, 24, int(np.argmax(r["peak"][b, 24]))]) == 16367
                 else:
                     assert (r["doppler"][nb - 1, 24], r["code_phase"][nb - 1, 24]) == (1500.0, 16367)
-            out["per_cell" if mode is None else "best_bin"] = {"value": nb * n / sec / 1e6, "seconds_per_job": sec, **search.last_bytes}
-        res.update({"scaling": "strong", "value": out["per_cell"]["value"],
-                    "e2e": {"value": out["per_cell"]["value"], "unit": "Msamples/s", "seconds_per_job": out["per_cell"]["seconds_per_job"],
-                            "h2d_bytes_per_job": out["per_cell"]["h2d"], "d2h_bytes_per_job": out["per_cell"]["d2h"],
-                            "nccl_scatter_bytes": out["per_cell"]["scatter"], "nccl_gather_bytes": out["per_cell"]["gather"],
-                            "api": "ShardedBlockSearch: rank-0 host -> scatter -> grid per rank -> gather -> rank-0 host"},
+            out[key] = {"value": nb * n / sec / 1e6, "seconds_per_job": sec, **search.last_bytes}
+        pc = out["per_cell"]
+        res.update({"scaling": "strong", "value": pc["value"],
+                    "e2e": {"value": pc["value"], "unit": "Msamples/s", "seconds_per_job": pc["seconds_per_job"],
+                            "h2d_bytes_per_job": pc["h2d"], "d2h_bytes_per_job": pc["d2h"],
+                            "nccl_scatter_bytes": pc["scatter"], "nccl_gather_bytes": pc["gather"],
+                            "api": "ShardedBlockSearch: rank-0 host -> one scatter -> grid per rank -> one gather -> rank-0 host"},
                     "with_on_device_best_bin_reduction": out["best_bin"],
                     "note": "fixed 1000-block job; compare `value` across N for strong-scaling efficiency; the N = 1 figure is configs.config5.e2e of the 1-GPU run"})
     eng.close()

@@ -807,11 +807,15 @@ int gb200_acquire_grid_host(gb200_engine* e, const float* iq_host, int n_blocks,
                       g.iq_dev == e->iq_own.p && g.rec_dev == e->d_records.p && g.iq_stage == e->h_iq.p &&
                       g.rec_stage == e->h_records.p && g.spec == e->spec.p && g.stream == e->stream &&
                       memcmp(g.dop.data(), dop, sizeof(double) * D) == 0 && memcmp(g.prn.data(), prn_idx, sizeof(int) * P) == 0;
+    // Small grids: the correlate kernel stores its 32-byte records straight into the pinned (device-mapped under UVA) staging
+    // buffer -- posted PCIe writes at the kernel's tail instead of a separate copy node behind it.
+    const bool direct = n_rec * sizeof(CellRecord) <= (256u << 10);
     auto enqueue = [&]() -> int {
         GB_CUDA(e, cudaMemcpyAsync(e->iq_own.p, e->h_iq.p, n_iq * sizeof(float2), cudaMemcpyHostToDevice, e->stream));
-        int rc = run_grid(e, n_blocks, M, prn_idx, P, dop, D, kind, e->d_records.p);
+        int rc = run_grid(e, n_blocks, M, prn_idx, P, dop, D, kind, direct ? e->h_records.p : e->d_records.p);
         if (rc) return rc;
-        GB_CUDA(e, cudaMemcpyAsync(e->h_records.p, e->d_records.p, n_rec * sizeof(CellRecord), cudaMemcpyDeviceToHost, e->stream));
+        if (!direct)
+            GB_CUDA(e, cudaMemcpyAsync(e->h_records.p, e->d_records.p, n_rec * sizeof(CellRecord), cudaMemcpyDeviceToHost, e->stream));
         return GB200_OK;
     };
     if (same && g.exec) {

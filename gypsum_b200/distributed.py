@@ -95,7 +95,7 @@ class ShardedGridSearch:
 class ShardedBlockSearch:
     """Many independent blocks (BASELINE config 5: 1000 x 1-ms blocks over 8 GPUs): rank 0 holds the IQ on its host, each
     rank receives only its contiguous share of blocks (one scatter), searches the full PRN x Doppler grid on them, and the
-    records come back to rank 0's host with one gather.  Buffers (device share, pinned host staging on rank 0) are kept
+    records come back to rank 0's host with one gather.  Buffers (device shares, the pinned receive buffer on rank 0) are kept
     between calls of the same shape.  `last_bytes` reports what the last call moved: host->device and device->host on rank
     0, scatter / gather payload over the interconnect (bytes leaving / reaching rank 0, its own share excluded)."""
 
@@ -123,15 +123,16 @@ class ShardedBlockSearch:
             if self.rank == 0:
                 self._all_iq = torch.empty(self.world * most * per_block, dtype=torch.float32, device=self.device)
                 self._all_out = torch.empty(self.world * most * row_bytes, dtype=torch.uint8, device=self.device)
-                self._h_iq = torch.empty(self.world * most * per_block, dtype=torch.float32, pin_memory=cuda)
                 self._h_out = torch.empty(self.world * most * row_bytes, dtype=torch.uint8, pin_memory=cuda)
             self._shape = shape
         return self._mine, self._out
 
-    def acquire_blocks(self, iq, n_blocks: int, ms_per_block: int, prn_idx, doppler_hz, kind: int, reduce: str | None = None):
-        """iq: complex64[n_blocks * ms_per_block * N] on rank 0 (ignored elsewhere).  Returns on rank 0 the record array
-        [n_blocks, n_prn, n_doppler] (RECORD_DTYPE), or with reduce="best" the array [n_blocks, n_prn] (BEST_DTYPE) of
-        acquisition.py:179-189 per row; None on the other ranks."""
+    def acquire_blocks(self, iq, n_blocks: int, ms_per_block: int, prn_idx, doppler_hz, kind: int, reduce: str | None = None,
+                       copy: bool = True):
+        """iq: complex64[n_blocks * ms_per_block * N] on rank 0 (ignored elsewhere; DMA'd in place when it lives in pinned
+        memory).  Returns on rank 0 the record array [n_blocks, n_prn, n_doppler] (RECORD_DTYPE), or with reduce="best" the
+        array [n_blocks, n_prn] (BEST_DTYPE) of acquisition.py:179-189 per row; None on the other ranks.  copy=False hands
+        out a view of the pinned receive buffer when the shares are equal (valid until the next call)."""
         import torch
 
         from gypsum_b200._native import BEST_DTYPE, RECORD_DTYPE
@@ -150,11 +151,15 @@ class ShardedBlockSearch:
         # ---- one scatter of equal-sized (padded) shares ----
         if self.rank == 0:
             words = np.ascontiguousarray(iq, dtype=np.complex64)[: n_blocks * per_block // 2].view(np.float32)
-            h = self._h_iq.numpy().reshape(self.world, most * per_block)
-            for r, s in enumerate(shares):  # (a contiguous copy when the shares are equal)
-                h[r, : len(s) * per_block] = words[s.start * per_block: s.stop * per_block]
-            self._all_iq.copy_(self._h_iq, non_blocking=cuda)
-            self.dist.scatter(mine, list(self._all_iq.view(self.world, -1).unbind(0)), src=0, group=self.group)
+            src = torch.from_numpy(words)
+            nb_ = cuda and src.is_pinned()  # pinned caller memory: asynchronous DMA straight from it, no staging copy
+            rows = self._all_iq.view(self.world, most * per_block)
+            if all(len(s) == most for s in shares):
+                self._all_iq.copy_(src, non_blocking=nb_)
+            else:
+                for r, s in enumerate(shares):
+                    rows[r, : len(s) * per_block].copy_(src[s.start * per_block: s.stop * per_block], non_blocking=nb_)
+            self.dist.scatter(mine, list(rows.unbind(0)), src=0, group=self.group)
         else:
             self.dist.scatter(mine, None, src=0, group=self.group)
 
@@ -183,10 +188,11 @@ class ShardedBlockSearch:
             return None
         dtype = BEST_DTYPE if reduce else RECORD_DTYPE
         tail = (prn.size,) if reduce else (prn.size, dop.size)
-        g = self._h_out.numpy().view(dtype).reshape((self.world, most) + tail)
+        raw = self._h_out.numpy()  # bytes: numpy copies structured records field by field, raw bytes with memcpy
         if all(len(s) == most for s in shares):
-            return g.reshape((n_blocks,) + tail).copy()
-        full = np.empty((n_blocks,) + tail, dtype=dtype)
+            flat = raw[: n_blocks * row_bytes]
+            return (flat.copy() if copy else flat).view(dtype).reshape((n_blocks,) + tail)
+        full = np.empty(n_blocks * row_bytes, dtype=np.uint8)
         for r, s in enumerate(shares):
-            full[s.start:s.stop] = g[r, : len(s)]
-        return full
+            full[s.start * row_bytes: s.stop * row_bytes] = raw[r * most * row_bytes: (r * most + len(s)) * row_bytes]
+        return full.view(dtype).reshape((n_blocks,) + tail)

@@ -11,6 +11,7 @@ state and histories the rest of gypsum reads.
 from __future__ import annotations
 
 import collections
+import math
 from dataclasses import dataclass
 from enum import Enum, auto
 
@@ -121,32 +122,42 @@ def _replica_index(ent, satellite, n: int) -> int:
     return POOL.replica_index(ent, chips)
 
 
-def _apply_record(params: GpsSatelliteTrackingParameters, rec, profile=None) -> None:
+# A record travels through this module as the plain tuple `np.void.item()` gives (one conversion per record instead of one
+# numpy scalar per field: with 32 trackers asked once per millisecond the host glue is what limits the drop-in path).
+_F = {name: i for i, name in enumerate(_native.TRACK_DTYPE.names)}
+(_DOPPLER, _CPHASE, _ERROR, _DISC, _PHASE_ACC, _DOPPLER_HIST, _CPHASE_HIST, _PEAK_RE, _PEAK_IM, _STRENGTH, _CODE_PHASE, _SYMBOL,
+ _LOCKED, _LOST) = (_F[k] for k in ("doppler", "carrier_phase", "error", "disc", "phase_acc", "doppler_hist", "carrier_phase_hist",
+                                    "peak_re", "peak_im", "strength", "code_phase", "symbol", "locked", "lost"))
+
+
+def _apply_record(params: GpsSatelliteTrackingParameters, rec: tuple, profile=None) -> None:
     """What tracker.py:299-387 appends / assigns during one process_samples call."""
-    peak = complex(float(rec["peak_re"]), float(rec["peak_im"]))
-    params.current_prn_code_phase_shift = int(rec["code_phase"])
-    params.discriminators.append(float(rec["disc"]))
+    peak = complex(rec[_PEAK_RE], rec[_PEAK_IM])
+    params.current_prn_code_phase_shift = rec[_CODE_PHASE]
+    params.discriminators.append(rec[_DISC])
     params.discriminators.append(0)  # tracker.py:305 self.accumulator
     if profile is not None:
         params.non_coherent_correlation_profiles.append(profile)
     params.correlation_peaks_rolling_buffer.append(peak)
-    params.correlation_peak_strengths_rolling_buffer.append(float(rec["strength"]))
-    params.carrier_wave_phase_errors.append(float(rec["error"]))
-    params.correlation_peak_angles.append(float(np.angle(peak)))
+    params.correlation_peak_strengths_rolling_buffer.append(rec[_STRENGTH])
+    params.carrier_wave_phase_errors.append(rec[_ERROR])
+    params.correlation_peak_angles.append(math.atan2(peak.imag, peak.real))  # np.angle
     # tracker.py:352-353 append the loop state to the histories BEFORE the 6-second constellation adjustment of :370-387;
     # current_* end up with the adjusted values
-    params.doppler_shifts.append(float(rec["doppler_hist"]))
-    params.carrier_wave_phases.append(float(rec["carrier_phase_hist"]))
-    params.current_carrier_wave_phase_shift = float(rec["carrier_phase"])
-    params.current_doppler_shift = float(rec["doppler"])
-    params._last_is_locked = bool(rec["locked"])
+    params.doppler_shifts.append(rec[_DOPPLER_HIST])
+    params.carrier_wave_phases.append(rec[_CPHASE_HIST])
+    params.current_carrier_wave_phase_shift = rec[_CPHASE]
+    params.current_doppler_shift = rec[_DOPPLER]
+    params._last_is_locked = bool(rec[_LOCKED])
 
 
 def _pseudosymbol(rec, start_time: float, end_time: float) -> EmittedPseudosymbol:
-    delay = (int(rec["code_phase"]) / 2046) * ONE_MILLISECOND  # tracker.py:319
+    if not isinstance(rec, tuple):
+        rec = rec.item()
+    delay = (rec[_CODE_PHASE] / 2046) * ONE_MILLISECOND  # tracker.py:319
     return EmittedPseudosymbol(
         start_of_pseudosymbol=start_time + delay, end_of_pseudosymbol=end_time + delay,
-        pseudosymbol=NavigationBitPseudosymbol.from_val(int(rec["symbol"])), cursor_at_emit_time=0)
+        pseudosymbol=NavigationBitPseudosymbol.from_val(rec[_SYMBOL]), cursor_at_emit_time=0)
 
 
 def _chunk_key(chunk) -> tuple:
@@ -227,9 +238,10 @@ class _ChannelPool:
         self._load(chunk, key)
         got = self.native.process_channels(sel, 1, [float(chunk.start_time)], want_profiles=profs, keep_undo=True)
         recs, prof = got if profs else (got, None)
+        rows = recs[:, 0].tolist()  # one tuple of Python scalars per channel
         for i, c in enumerate(sel[1:], start=1):
-            self.ahead[c] = (key, recs[i, 0].copy(), None if prof is None else prof[i, 0])
-        return recs[0, 0].copy(), (None if prof is None else prof[0, 0])
+            self.ahead[c] = (key, rows[i], None if prof is None else prof[i, 0])
+        return rows[0], (None if prof is None else prof[0, 0])
 
 
 def _pool_of(ent) -> _ChannelPool:
@@ -292,15 +304,15 @@ class GpsSatelliteTracker:
         """tracker.py:331-389."""
         self._push_host_edits()
         rec, prof = self._pool.step(self._channel, receiver_samples_chunk, self.keep_correlation_profiles)
-        if int(rec["lost"]) >= 2:  # cannot happen through this class (the flag is cleared above); never hand out a placeholder
+        if rec[_LOST] >= 2:  # cannot happen through this class (the flag is cleared above); never hand out a placeholder
             raise LostSatelliteLockError()
-        if int(rec["symbol"]) == 0:
+        if rec[_SYMBOL] == 0:
             raise KeyError(0)  # tracker.py:317: NavigationBitPseudosymbol.from_val has no entry for 0
         keep = self.keep_correlation_profiles and prof is not None
         _apply_record(self.tracking_params, rec, prof.astype(np.float64) if keep else None)
-        self.phase = float(rec["phase_acc"])
+        self.phase = rec[_PHASE_ACC]
         self._device_view = self._host_view()
-        if int(rec["lost"]):
+        if rec[_LOST]:
             self._pool.stopped.add(self._channel)
             raise LostSatelliteLockError()  # tracker.py:378
         return _pseudosymbol(rec, receiver_samples_chunk.start_time, receiver_samples_chunk.end_time)

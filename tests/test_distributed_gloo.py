@@ -90,7 +90,10 @@ def _block_worker(rank, world, port, q):
     full = search.acquire_blocks(x, 5, 1, np.array([8, 0]), [-500.0, 0.0], 2)
     moved = dict(search.last_bytes)
     best = search.acquire_blocks(x, 5, 1, np.array([8, 0]), [-500.0, 0.0], 2, reduce="best")
-    q.put((rank, None if full is None else (full["peak"].copy(), full["argmax"].copy(), best.copy(), moved, dict(search.last_bytes))))
+    moved_best = search.last_bytes
+    view = search.acquire_blocks(x, 5, 1, np.array([8, 0]), [-500.0, 0.0], 2, copy=False)
+    assert view is None or np.array_equal(view["peak"], full["peak"])
+    q.put((rank, None if full is None else (full["peak"].copy(), full["argmax"].copy(), best.copy(), moved, dict(moved_best))))
     dist.destroy_process_group()
 
 
