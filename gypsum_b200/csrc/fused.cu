@@ -88,39 +88,40 @@ __global__ void __launch_bounds__(2 * S * 32, (S == 2 ? 3 : 1)) k_acquire_fused(
         if (tid < S) ypoly[tid * kFft + (kFft - 1)] = ypoly[tid * kFft];
         __syncthreads();
 
-        float re[32], im[32];
-        build_z(re, im, lane, r, S, ypoly);
+        float2 x[32];
+        build_z(x, lane, r, S, ypoly);
         __syncthreads();  // every warp is done with ypoly; the next millisecond may overwrite it
+        // forward transform, spectrum product, inverse transform as conj(forward(conj(.))): one copy of the warp-FFT code
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
             if (pass == 0) {
-                if (h) mul_tw2(re, im, lane, tw2_s);
+                if (h) mul_tw2(x, lane, tw2_s);
             } else {
-                mul_vec(re, im, lane, crep_s + h * kFft);
+                mul_vec(x, lane, crep_s + h * kFft);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) im[j] = -im[j];
+                for (int j = 0; j < 32; ++j) x[j].y = -x[j].y;
             }
-            wfft_phase1(re, im, lane, tw1_s, tile);
+            wfft_phase1<false>(x, lane, tw1_s, tile);
             __syncwarp();
-            wfft_phase2(re, im, lane, tile);
+            wfft_phase2<false>(x, lane, tile);
             __syncwarp();
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) im[j] = -im[j];
-        exchange_store(re, im, lane, h, tile);
+        for (int j = 0; j < 32; ++j) x[j].y = -x[j].y;
+        exchange_store(x, lane, h, tile);
         pair_barrier(r);
-        float xr[16], xi[16];
-        if (h == 0) combine_even(re, im, lane, tw2_s, ptile, xr, xi);
-        else combine_odd(re, im, lane, tw2_s, ptile, xr, xi);
+        float2 out16[16];
+        if (h == 0) combine_even(x, lane, tw2_s, ptile, out16);
+        else combine_odd(x, lane, tw2_s, ptile, out16);
         if (KIND == kKindCoherent) {
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) {
-                acc_re[jj] += xr[jj];  // utils.py:102: the complex correlation is summed over the milliseconds
-                acc_im[jj] += xi[jj];
+                acc_re[jj] += out16[jj].x;  // utils.py:102: the complex correlation is summed over the milliseconds
+                acc_im[jj] += out16[jj].y;
             }
         } else {
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) acc_re[jj] += gb_mag(xr[jj], xi[jj]);  // utils.py:104
+            for (int jj = 0; jj < 16; ++jj) acc_re[jj] += gb_mag(out16[jj]);  // utils.py:104
         }
         // the next millisecond's CTA-wide barriers order the tile reuse
     }
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(2 * S * 32, (S == 2 ? 3 : 1)) k_acquire_fused(
 #pragma unroll
     for (int jj = 0; jj < 16; ++jj) {
         if (KIND == kKindCoherent) {
-            v[jj] = gb_mag(acc_re[jj], acc_im[jj]);
+            v[jj] = gb_mag(make_float2(acc_re[jj], acc_im[jj]));
             const int q = lane + 32 * (16 * h + jj);
             if (q < kChips && S * q + r == probe) {
                 pr_re = acc_re[jj];

@@ -131,15 +131,15 @@ __global__ void __launch_bounds__(spec_warps(S) * 32, S == 2 ? 5 : 1) k_doppler_
     float2* __restrict__ dst0 = a.spec + (static_cast<size_t>(unit) * a.M + i) * S * 2 * kFft;
     for (int task = warp; task < 2 * S; task += kSpecWarps) {
         const int r = task >> 1, half = task & 1;
-        float re[32], im[32];
-        load_vec(re, im, lane, ypoly + r * kFft);
+        float2 x[32];
+        load_vec(x, lane, ypoly + r * kFft);
         if (spec_alias(S)) __syncthreads();  // single pass (one task per warp): the rows are dead, the tiles may take their place
-        if (half) mul_tw2(re, im, lane, a.tw2);
-        wfft_phase1(re, im, lane, a.tw1, tile);
+        if (half) mul_tw2(x, lane, a.tw2);
+        wfft_phase1<false>(x, lane, a.tw1, tile);
         __syncwarp();
-        wfft_phase2(re, im, lane, tile);
+        wfft_phase2<false>(x, lane, tile);
         __syncwarp();
-        store_vec(re, im, lane, dst0 + static_cast<size_t>(task) * kFft);
+        store_vec(x, lane, dst0 + static_cast<size_t>(task) * kFft);
     }
 }
 
@@ -271,59 +271,56 @@ __global__ void __launch_bounds__(NP * 64, 1) k_correlate_cells(const CorrelateA
                 // with the trip count known the accumulators are not live across the transform and nothing spills.
                 const int n_iter = (KIND == kKindCoherent || NP == 10) ? 1 : a.M;
                 for (int it = 0; it < n_iter; ++it) {
-                    float re[32], im[32];
+                    float2 x[32];
                     if (KIND == kKindCoherent) {
                         // Coherent integration (utils.py:102) commutes with the linear correlation: sum the
                         // M spectra first, transform once.
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) re[j] = im[j] = 0.f;
+                        for (int j = 0; j < 32; ++j) x[j] = make_float2(0.f, 0.f);
                         for (int i = 0; i < a.M; ++i) {
                             const float2* __restrict__ p = spec_u + (static_cast<size_t>(i * a.s + r) * 2 + h) * kFft;
 #pragma unroll
                             for (int jp = 0; jp < 16; ++jp) {
                                 float2 v0, v1;
                                 ld_pair(p + 2 * (jp * 32 + lane), v0, v1);
-                                re[2 * jp] += v0.x;
-                                im[2 * jp] += v0.y;
-                                re[2 * jp + 1] += v1.x;
-                                im[2 * jp + 1] += v1.y;
+                                x[2 * jp] = c_add(x[2 * jp], v0);
+                                x[2 * jp + 1] = c_add(x[2 * jp + 1], v1);
                             }
                         }
-                        mul_vec(re, im, lane, crep_h);
+                        mul_vec(x, lane, crep_h);
                     } else {
                         const float2* __restrict__ p = spec_u + (static_cast<size_t>(it * a.s + r) * 2 + h) * kFft;
-                        load_mul_vec(re, im, lane, p, crep_h);
+                        load_mul_vec(x, lane, p, crep_h);
                     }
-                    // inverse warp FFT-1024 = forward transform on swapped re/im
-                    wfft_phase1(im, re, lane, tw1_s, tile);
+                    wfft_phase1<true>(x, lane, tw1_s, tile);  // inverse warp FFT-1024
                     __syncwarp();
-                    wfft_phase2(im, re, lane, tile);
+                    wfft_phase2<true>(x, lane, tile);
                     __syncwarp();
-                    exchange_store(re, im, lane, h, tile);
+                    exchange_store(x, lane, h, tile);
                     pair_barrier(pair);
-                    float xr[16], xi[16];
-                    if (h == 0) combine_even(re, im, lane, tw2_s, ptile, xr, xi);
-                    else combine_odd(re, im, lane, tw2_s, ptile, xr, xi);
+                    float2 out16[16];
+                    if (h == 0) combine_even(x, lane, tw2_s, ptile, out16);
+                    else combine_odd(x, lane, tw2_s, ptile, out16);
                     if (KIND == kKindCoherent) {
 #pragma unroll
                         for (int jj = 0; jj < 16; ++jj) {
-                            acc[jj] = gb_mag(xr[jj], xi[jj]);
+                            acc[jj] = gb_mag(out16[jj]);
                             const int q = lane + 32 * (16 * h + jj);
                             const int n = a.s * q + r;
                             if (n == probe && q < kChips) {
-                                pr_re = xr[jj];
-                                pr_im = xi[jj];
+                                pr_re = out16[jj].x;
+                                pr_im = out16[jj].y;
                             }
                             if (PROFILE) {
                                 if (q < kChips) {
-                                    a.profile[2 * n] = xr[jj];
-                                    a.profile[2 * n + 1] = xi[jj];
+                                    a.profile[2 * n] = out16[jj].x;
+                                    a.profile[2 * n + 1] = out16[jj].y;
                                 }
                             }
                         }
                     } else {
 #pragma unroll
-                        for (int jj = 0; jj < 16; ++jj) acc[jj] += gb_mag(xr[jj], xi[jj]);
+                        for (int jj = 0; jj < 16; ++jj) acc[jj] += gb_mag(out16[jj]);
                     }
                     pair_barrier(pair);  // partner has read my tile; the next phase 1 may overwrite it
                 }
@@ -495,21 +492,21 @@ __global__ void __launch_bounds__(NW * 32, 1) k_correlate_w2048(const CorrelateA
                 for (int it = 0; it < n_iter; ++it) {
                     const float2* __restrict__ p = spec_u + static_cast<size_t>(it * a.s + r) * 2 * kFft;
                     {
-                        float hr[32], hi[32];
-                        load_mul_vec(hr, hi, lane, p, crep_s);  // even bins
-                        w2048_phase1<0>(hi, hr, lane, tw1_s, tile);  // inverse = forward on swapped re/im
+                        float2 hx[32];
+                        load_mul_vec(hx, lane, p, crep_s);  // even bins
+                        w2048_phase1<0>(hx, lane, tw1_s, tile);
                     }
                     {
-                        float hr[32], hi[32];
-                        load_mul_vec(hr, hi, lane, p + kFft, crep_s + kFft);  // odd bins
-                        w2048_phase1<1>(hi, hr, lane, tw1_s, tile);
+                        float2 hx[32];
+                        load_mul_vec(hx, lane, p + kFft, crep_s + kFft);  // odd bins
+                        w2048_phase1<1>(hx, lane, tw1_s, tile);
                     }
                     __syncwarp();
-                    float re[64], im[64];
-                    w2048_phase2(im, re, lane, tile);
+                    float2 x[64];
+                    w2048_phase2(x, lane, tile);
                     __syncwarp();  // the tile may be overwritten by the next transform
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) acc[k] += gb_mag(re[k], im[k]);
+                    for (int k = 0; k < 32; ++k) acc[k] += gb_mag(x[k]);
                 }
                 // lags q = lane + 32 k: k < 16 and k >= 16 are the two halves thread_peak16 knows as h = 0 / 1
 #pragma unroll

@@ -135,31 +135,31 @@ __global__ void __launch_bounds__(kTrackThreads, 1) k_track_channels(const Track
         __syncthreads();
 
         if (warp < n_fft_warps) {
-            float re[32], im[32];
+            float2 x[32];
             // forward transform, spectrum product, inverse transform (= conj, forward, conj): one copy of the
             // warp-FFT code serves both passes.
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {
                 if (pass == 0) {
-                    build_z(re, im, lane, r, S, ypoly);
-                    if (h) mul_tw2(re, im, lane, tw2_s);
+                    build_z(x, lane, r, S, ypoly);
+                    if (h) mul_tw2(x, lane, tw2_s);
                 } else {
-                    mul_vec(re, im, lane, crep_s + h * kFft);
+                    mul_vec(x, lane, crep_s + h * kFft);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) im[j] = -im[j];
+                    for (int j = 0; j < 32; ++j) x[j].y = -x[j].y;
                 }
-                wfft_phase1(re, im, lane, tw1_s, tile);
+                wfft_phase1<false>(x, lane, tw1_s, tile);
                 __syncwarp();
-                wfft_phase2(re, im, lane, tile);
+                wfft_phase2<false>(x, lane, tile);
                 __syncwarp();
             }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) im[j] = -im[j];
-            exchange_store(re, im, lane, h, tile);
+            for (int j = 0; j < 32; ++j) x[j].y = -x[j].y;
+            exchange_store(x, lane, h, tile);
             pair_barrier(r);
-            float xr[16], xi[16];
-            if (h == 0) combine_even(re, im, lane, tw2_s, ptile, xr, xi);
-            else combine_odd(re, im, lane, tw2_s, ptile, xr, xi);
+            float2 out16[16];
+            if (h == 0) combine_even(x, lane, tw2_s, ptile, out16);
+            else combine_odd(x, lane, tw2_s, ptile, out16);
 
             // ---- prompt profile statistics in rolled order (tracker.py:308-313), early / late taps ----
             float mx = -1.f, sum = 0.f, bre = 0.f, bim = 0.f;
@@ -169,21 +169,21 @@ __global__ void __launch_bounds__(kTrackThreads, 1) k_track_channels(const Track
                 const int q = lane + 32 * (16 * h + jj);
                 if (q < kChips) {
                     const int n = S * q + r;
-                    const float v = gb_mag(xr[jj], xi[jj]);
+                    const float v = gb_mag(out16[jj]);
                     int kk = n - pm;
                     kk = kk < 0 ? kk + a.N : kk;
                     if (v > mx || (v == mx && kk < key)) {
                         cnt = v > mx ? 1 : cnt + 1;
                         mx = v;
                         key = kk;
-                        bre = xr[jj];
-                        bim = xi[jj];
+                        bre = out16[jj].x;
+                        bim = out16[jj].y;
                     } else if (v == mx) {
                         cnt++;
                     }
                     sum += v;
-                    if (n == kE) el[0] = make_float2(xr[jj], xi[jj]);
-                    if (n == kL) el[1] = make_float2(xr[jj], xi[jj]);
+                    if (n == kE) el[0] = out16[jj];
+                    if (n == kL) el[1] = out16[jj];
                     if (a.profiles) a.profiles[(static_cast<size_t>(slot) * a.n_ms + k) * a.N + kk] = v;
                 }
             }

@@ -15,24 +15,16 @@
 // A warp transform holds x[lane + 32 j] in registers: FFT-32 over j, twiddle W1024^(lane*k1), 32x32 transpose
 // through a padded shared tile, FFT-32 over lane.  Output X[lane + 32 k2] lands in the same layout.
 #pragma once
+#include "cplx2.cuh"
 #include "fft32_gen.cuh"
 #include "gb_common.cuh"
 
 namespace gb {
 
-// Every multiply-add on the data path is an explicit fmaf(): the rounding of a product-sum must not depend on which
-// contraction the compiler happens to pick in a given inlining context -- all kernels (and the host lane emulator) that
-// run the same sequence of operations then agree bit for bit, which the parity tests rely on.
-GB_HD GB_INLINE float2 cmul(float2 a, float2 b) {
-    return make_float2(fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x));
-}
-GB_HD GB_INLINE float2 cmulc(float2 a, float2 b) {  // a * conj(b)
-    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -(a.x * b.y)));
-}
-// e + o * conj(w), two FMAs per component
-GB_HD GB_INLINE float2 cfmac(float2 e, float2 o, float2 w) {
-    return make_float2(fmaf(o.x, w.x, fmaf(o.y, w.y, e.x)), fmaf(o.y, w.x, fmaf(-o.x, w.y, e.y)));
-}
+// Complex values are float2 = (re, im) and all complex arithmetic goes through cplx2.cuh (packed FADD2 / FMUL2 / FFMA2 on the
+// device, the same IEEE operations lane by lane on the host): the rounding of a product-sum never depends on a contraction
+// the compiler happens to pick in a given inlining context -- all kernels (and the host lane emulator) that run the same
+// sequence of operations agree bit for bit, which the parity tests rely on.
 
 // Pair-interleaved layout used by every per-thread table and vector (spectra, replica spectra, twiddles, exchange
 // tiles, polyphase rows): element j of lane `lane` (i.e. logical index lane + 32 j) sits at pidx(j, lane), so a thread's
@@ -60,77 +52,60 @@ GB_HD GB_INLINE void st_pair(float2* p, float2 a, float2 b) {
 #endif
 }
 
-// Phase 1 of the forward warp FFT-1024.  re/im[j] = x[lane + 32 j].  Writes u[lane][k1]*W1024^(lane k1) to the
-// tile, row k1, column lane.  tw1[pidx(k1, lane)] = exp(-2 pi i lane k1 / 1024).
-GB_HD GB_INLINE void wfft_phase1(float (&re)[32], float (&im)[32], int lane, const float2* tw1, float2* tile) {
-    fft32_fwd(re, im);
+// Phase 1 of the warp FFT-1024.  x[j] = x[lane + 32 j].  Writes u[lane][k1] * W1024^(+-lane k1) to the tile, row k1, column
+// lane.  tw1[pidx(k1, lane)] = exp(-2 pi i lane k1 / 1024); the inverse multiplies by its conjugate.
+template <bool INV>
+GB_HD GB_INLINE void wfft_phase1(float2 (&x)[32], int lane, const float2* tw1, float2* tile) {
+    if (INV) fft32_inv(x);
+    else fft32_fwd(x);
 #pragma unroll
     for (int kp = 0; kp < 16; ++kp) {
         float2 w0, w1;
         ld_pair(tw1 + 2 * (kp * 32 + lane), w0, w1);
         const int k1 = 2 * kp;
-        if (kp == 0) tile[lane] = make_float2(re[0], im[0]);
-        else tile[k1 * kTStride + lane] = cmul(make_float2(re[k1], im[k1]), w0);
-        tile[(k1 + 1) * kTStride + lane] = cmul(make_float2(re[k1 + 1], im[k1 + 1]), w1);
+        if (kp == 0) tile[lane] = x[0];
+        else tile[k1 * kTStride + lane] = INV ? cmulc(x[k1], w0) : cmul(x[k1], w0);
+        tile[(k1 + 1) * kTStride + lane] = INV ? cmulc(x[k1 + 1], w1) : cmul(x[k1 + 1], w1);
     }
 }
 // Phase 2: thread `lane` owns column k1 = lane: reads u[l][lane], l = 0..31, FFT-32 over l.  Afterwards
-// re/im[k2] = X[lane + 32 k2].
-GB_HD GB_INLINE void wfft_phase2(float (&re)[32], float (&im)[32], int lane, const float2* tile) {
+// x[k2] = X[lane + 32 k2].
+template <bool INV>
+GB_HD GB_INLINE void wfft_phase2(float2 (&x)[32], int lane, const float2* tile) {
 #pragma unroll
-    for (int lp = 0; lp < 16; ++lp) {
-        float2 v0, v1;
-        ld_pair(tile + lane * kTStride + 2 * lp, v0, v1);
-        re[2 * lp] = v0.x;
-        im[2 * lp] = v0.y;
-        re[2 * lp + 1] = v1.x;
-        im[2 * lp + 1] = v1.y;
-    }
-    fft32_fwd(re, im);
+    for (int lp = 0; lp < 16; ++lp) ld_pair(tile + lane * kTStride + 2 * lp, x[2 * lp], x[2 * lp + 1]);
+    if (INV) fft32_inv(x);
+    else fft32_fwd(x);
 }
 
 // registers <-> a pair-interleaved vector (global or shared)
-GB_HD GB_INLINE void load_vec(float (&re)[32], float (&im)[32], int lane, const float2* v) {
+GB_HD GB_INLINE void load_vec(float2 (&x)[32], int lane, const float2* v) {
 #pragma unroll
-    for (int jp = 0; jp < 16; ++jp) {
-        float2 a, b;
-        ld_pair(v + 2 * (jp * 32 + lane), a, b);
-        re[2 * jp] = a.x;
-        im[2 * jp] = a.y;
-        re[2 * jp + 1] = b.x;
-        im[2 * jp + 1] = b.y;
-    }
+    for (int jp = 0; jp < 16; ++jp) ld_pair(v + 2 * (jp * 32 + lane), x[2 * jp], x[2 * jp + 1]);
 }
-GB_HD GB_INLINE void store_vec(const float (&re)[32], const float (&im)[32], int lane, float2* v) {
+GB_HD GB_INLINE void store_vec(const float2 (&x)[32], int lane, float2* v) {
 #pragma unroll
-    for (int jp = 0; jp < 16; ++jp)
-        st_pair(v + 2 * (jp * 32 + lane), make_float2(re[2 * jp], im[2 * jp]), make_float2(re[2 * jp + 1], im[2 * jp + 1]));
+    for (int jp = 0; jp < 16; ++jp) st_pair(v + 2 * (jp * 32 + lane), x[2 * jp], x[2 * jp + 1]);
 }
 // x[j] *= w[j] for a pair-interleaved vector w (spectrum product, twiddles)
-GB_HD GB_INLINE void mul_vec(float (&re)[32], float (&im)[32], int lane, const float2* w) {
+GB_HD GB_INLINE void mul_vec(float2 (&x)[32], int lane, const float2* w) {
 #pragma unroll
     for (int jp = 0; jp < 16; ++jp) {
         float2 a, b;
         ld_pair(w + 2 * (jp * 32 + lane), a, b);
-        const float2 p0 = cmul(make_float2(re[2 * jp], im[2 * jp]), a), p1 = cmul(make_float2(re[2 * jp + 1], im[2 * jp + 1]), b);
-        re[2 * jp] = p0.x;
-        im[2 * jp] = p0.y;
-        re[2 * jp + 1] = p1.x;
-        im[2 * jp + 1] = p1.y;
+        x[2 * jp] = cmul(x[2 * jp], a);
+        x[2 * jp + 1] = cmul(x[2 * jp + 1], b);
     }
 }
-// re/im = a[j] * w[j]: load a pair-interleaved vector and multiply in one pass (half-spectrum x replica spectrum)
-GB_HD GB_INLINE void load_mul_vec(float (&re)[32], float (&im)[32], int lane, const float2* a, const float2* w) {
+// x = a[j] * w[j]: load a pair-interleaved vector and multiply in one pass (half-spectrum x replica spectrum)
+GB_HD GB_INLINE void load_mul_vec(float2 (&x)[32], int lane, const float2* a, const float2* w) {
 #pragma unroll
     for (int jp = 0; jp < 16; ++jp) {
         float2 a0, a1, w0, w1;
         ld_pair(a + 2 * (jp * 32 + lane), a0, a1);
         ld_pair(w + 2 * (jp * 32 + lane), w0, w1);
-        const float2 p0 = cmul(a0, w0), p1 = cmul(a1, w1);
-        re[2 * jp] = p0.x;
-        im[2 * jp] = p0.y;
-        re[2 * jp + 1] = p1.x;
-        im[2 * jp + 1] = p1.y;
+        x[2 * jp] = cmul(a0, w0);
+        x[2 * jp + 1] = cmul(a1, w1);
     }
 }
 
@@ -167,38 +142,35 @@ GB_HD GB_INLINE void boxcar_column(const float2* ypoly, int m, float2 (&z)[S]) {
     float2 suf[S + 1];
     suf[S] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int t = S - 1; t >= 0; --t) suf[t] = make_float2(suf[t + 1].x + v[t].x, suf[t + 1].y + v[t].y);
+    for (int t = S - 1; t >= 0; --t) suf[t] = c_add(suf[t + 1], v[t]);
     float2 pre = make_float2(0.f, 0.f);
 #pragma unroll
     for (int r = 0; r < S; ++r) {
-        z[r] = make_float2(suf[r].x + pre.x, suf[r].y + pre.y);
-        pre = make_float2(pre.x + w[r].x, pre.y + w[r].y);
+        z[r] = c_add(suf[r], pre);
+        pre = c_add(pre, w[r]);
     }
 }
 
 // Polyphase boxcar computed directly (tracking kernel, s = 2 or 4): z_r[m] for m = lane + 32 j, from the wiped-off
 // millisecond stored linearly as ypoly[t][m'] = y[s*m' + t], row length 1024, ypoly[t][1023] = ypoly[t][0].
-GB_HD GB_INLINE void build_z(float (&re)[32], float (&im)[32], int lane, int r, int s, const float2* ypoly) {
+GB_HD GB_INLINE void build_z(float2 (&x)[32], int lane, int r, int s, const float2* ypoly) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
         const int m = lane + 32 * j;
-        float ar = 0.f, ai = 0.f;
+        float2 a = make_float2(0.f, 0.f);
         if (m < kChips) {
             for (int t = 0; t < s; ++t) {
                 const int rt = r + t;
                 const int row = rt >= s ? rt - s : rt;
-                const float2 v = ypoly[row * kFft + m + (rt >= s ? 1 : 0)];
-                ar += v.x;
-                ai += v.y;
+                a = c_add(a, ypoly[row * kFft + m + (rt >= s ? 1 : 0)]);
             }
         }
-        re[j] = ar;
-        im[j] = ai;
+        x[j] = a;
     }
 }
 
 // x[n] *= W2048^n (forward odd half) for n = lane + 32 j;  tw2[pidx(j, lane)] = exp(-2 pi i n / 2048), n < 1024.
-GB_HD GB_INLINE void mul_tw2(float (&re)[32], float (&im)[32], int lane, const float2* tw2) { mul_vec(re, im, lane, tw2); }
+GB_HD GB_INLINE void mul_tw2(float2 (&x)[32], int lane, const float2* tw2) { mul_vec(x, lane, tw2); }
 
 // Fast magnitude: MUFU.SQRT (sqrt.approx, ~1 ulp) on the device instead of the IEEE sequence with its slow path.
 GB_HD GB_INLINE float gb_sqrt(float x) {
@@ -211,55 +183,42 @@ GB_HD GB_INLINE float gb_sqrt(float x) {
 #endif
 }
 
-GB_HD GB_INLINE float gb_mag(float re, float im) { return gb_sqrt(fmaf(re, re, im * im)); }  // |re + j im|
+GB_HD GB_INLINE float gb_mag(float2 z) { return gb_sqrt(fmaf(z.x, z.x, z.y * z.y)); }  // |re + j im|
 
 // Radix-2 recombination of the two inverse half transforms, out[k] = E[k] + conj(W2048^k) O[k], split so both
 // warps of a pair do the same amount of work: the even-bin warp finishes lags k = lane + 32 jj (jj < 16) from
 // its own E and the partner's raw O; the odd-bin warp finishes k = lane + 32 (16 + jj) from its own O and the
 // partner's E.  `theirs` is the partner's exchange tile ([jj*32 + lane]).
-GB_HD GB_INLINE void combine_even(const float (&re)[32], const float (&im)[32], int lane, const float2* tw2,
-                                  const float2* theirs, float (&xr)[16], float (&xi)[16]) {
+GB_HD GB_INLINE void combine_even(const float2 (&x)[32], int lane, const float2* tw2, const float2* theirs, float2 (&out)[16]) {
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
         float2 o0, o1, w0, w1;
         ld_pair(theirs + 2 * (p * 32 + lane), o0, o1);
         ld_pair(tw2 + 2 * (p * 32 + lane), w0, w1);
-        const float2 x0 = cfmac(make_float2(re[2 * p], im[2 * p]), o0, w0);
-        const float2 x1 = cfmac(make_float2(re[2 * p + 1], im[2 * p + 1]), o1, w1);
-        xr[2 * p] = x0.x;
-        xi[2 * p] = x0.y;
-        xr[2 * p + 1] = x1.x;
-        xi[2 * p + 1] = x1.y;
+        out[2 * p] = cfmac(x[2 * p], o0, w0);
+        out[2 * p + 1] = cfmac(x[2 * p + 1], o1, w1);
     }
 }
-GB_HD GB_INLINE void combine_odd(const float (&re)[32], const float (&im)[32], int lane, const float2* tw2,
-                                 const float2* theirs, float (&xr)[16], float (&xi)[16]) {
+GB_HD GB_INLINE void combine_odd(const float2 (&x)[32], int lane, const float2* tw2, const float2* theirs, float2 (&out)[16]) {
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
         float2 e0, e1, w0, w1;
         ld_pair(theirs + 2 * (p * 32 + lane), e0, e1);
         ld_pair(tw2 + 2 * ((8 + p) * 32 + lane), w0, w1);
         const int j = 16 + 2 * p;
-        const float2 x0 = cfmac(e0, make_float2(re[j], im[j]), w0);
-        const float2 x1 = cfmac(e1, make_float2(re[j + 1], im[j + 1]), w1);
-        xr[2 * p] = x0.x;
-        xi[2 * p] = x0.y;
-        xr[2 * p + 1] = x1.x;
-        xi[2 * p + 1] = x1.y;
+        out[2 * p] = cfmac(e0, x[j], w0);
+        out[2 * p + 1] = cfmac(e1, x[j + 1], w1);
     }
 }
 // What each warp hands to its partner (pair-interleaved, [pidx(jj, lane)]): the even-bin warp its E[k] for the upper
 // lags, the odd-bin warp its raw O[k] for the lower lags.
-GB_HD GB_INLINE void exchange_store(const float (&re)[32], const float (&im)[32], int lane, int h, float2* mine) {
+GB_HD GB_INLINE void exchange_store(const float2 (&x)[32], int lane, int h, float2* mine) {
     if (h == 0) {
 #pragma unroll
-        for (int p = 0; p < 8; ++p)
-            st_pair(mine + 2 * (p * 32 + lane), make_float2(re[16 + 2 * p], im[16 + 2 * p]),
-                    make_float2(re[17 + 2 * p], im[17 + 2 * p]));
+        for (int p = 0; p < 8; ++p) st_pair(mine + 2 * (p * 32 + lane), x[16 + 2 * p], x[17 + 2 * p]);
     } else {
 #pragma unroll
-        for (int p = 0; p < 8; ++p)
-            st_pair(mine + 2 * (p * 32 + lane), make_float2(re[2 * p], im[2 * p]), make_float2(re[2 * p + 1], im[2 * p + 1]));
+        for (int p = 0; p < 8; ++p) st_pair(mine + 2 * (p * 32 + lane), x[2 * p], x[2 * p + 1]);
     }
 }
 
@@ -354,11 +313,12 @@ constexpr int kTile64F2 = 64 * kT64Stride;     // 64 rows (l') x 32 columns (k1)
     {9.965711458e-01f, -8.274026455e-02f}, {9.963126122e-01f, -8.579731234e-02f}, {9.960447009e-01f, -8.885355258e-02f}, \
     {9.957674145e-01f, -9.190895650e-02f}, {9.954807555e-01f, -9.496349533e-02f}
 
-// Phase 1 for one parity h: re/im[j] = Y_h[lane + 32 j].  tw1 is the W1024^(lane k1) table (pair-interleaved).
+// Phase 1 for one parity h of the INVERSE transform: x[j] = Y_h[lane + 32 j].  tw1 is the W1024^(lane k1) table
+// (pair-interleaved); the inverse multiplies by conjugates.
 template <int H>
-GB_HD GB_INLINE void w2048_phase1(float (&re)[32], float (&im)[32], int lane, const float2* tw1, float2* tile) {
+GB_HD GB_INLINE void w2048_phase1(float2 (&x)[32], int lane, const float2* tw1, float2* tile) {
     constexpr float kW[32][2] = {GB_W2048_TABLE};
-    fft32_fwd(re, im);
+    fft32_inv(x);
     float2* row = tile + (H * 32 + lane) * kT64Stride;  // physical row of l' = 2*lane + H
 #pragma unroll
     for (int kp = 0; kp < 16; ++kp) {
@@ -369,25 +329,21 @@ GB_HD GB_INLINE void w2048_phase1(float (&re)[32], float (&im)[32], int lane, co
             const int k1 = 2 * kp + q;
             float2 w = q ? w1 : w0;
             if (H == 1) w = cmul(w, make_float2(kW[k1][0], kW[k1][1]));
-            if (k1 == 0 && H == 0) row[0] = make_float2(re[0], im[0]);
-            else row[k1] = cmul(make_float2(re[k1], im[k1]), w);
+            if (k1 == 0 && H == 0) row[0] = x[0];
+            else row[k1] = cmulc(x[k1], w);
         }
     }
 }
 
-// Phase 2: thread `lane` owns column k1 = lane: gathers the 64 rows (l' natural order), FFT-64 over l'.
-// Afterwards re/im[k2] = X[lane + 32 k2]; only k2 < 32 are meaningful for the pruned transform.
-GB_HD GB_INLINE void w2048_phase2(float (&re)[64], float (&im)[64], int lane, const float2* tile) {
+// Phase 2: thread `lane` owns column k1 = lane: gathers the 64 rows (l' natural order), inverse FFT-64 over l'.
+// Afterwards x[k2] = X[lane + 32 k2]; only k2 < 32 are meaningful for the pruned transform.
+GB_HD GB_INLINE void w2048_phase2(float2 (&x)[64], int lane, const float2* tile) {
 #pragma unroll
     for (int p = 0; p < 32; ++p) {
-        const float2 e = tile[p * kT64Stride + lane];         // l' = 2p
-        const float2 o = tile[(32 + p) * kT64Stride + lane];  // l' = 2p + 1
-        re[2 * p] = e.x;
-        im[2 * p] = e.y;
-        re[2 * p + 1] = o.x;
-        im[2 * p + 1] = o.y;
+        x[2 * p] = tile[p * kT64Stride + lane];             // l' = 2p
+        x[2 * p + 1] = tile[(32 + p) * kT64Stride + lane];  // l' = 2p + 1
     }
-    fft64_fwd(re, im);
+    fft64_inv(x);
 }
 
 }  // namespace gb

@@ -31,7 +31,7 @@ def emu_lib():
 
     src = os.path.join(ROOT, "tests", "emu", "emu.cu")
     out = os.path.join(ROOT, "tests", "emu", "libgbemu.so")
-    deps = [src] + [os.path.join(ROOT, "gypsum_b200", "csrc", f) for f in ("warp_fft.cuh", "fft32_gen.cuh", "gb_common.cuh", "tracker_core.cuh", "bits_core.cuh")]
+    deps = [src] + [os.path.join(ROOT, "gypsum_b200", "csrc", f) for f in ("warp_fft.cuh", "fft32_gen.cuh", "cplx2.cuh", "gb_common.cuh", "tracker_core.cuh", "bits_core.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.run(["nvcc", "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-o", out, src], check=True,
                        capture_output=True)

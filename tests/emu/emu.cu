@@ -27,17 +27,17 @@ static void init_tables() {
 }
 
 struct WarpRegs {
-    float re[32][32], im[32][32];  // [lane][j]
+    float2 x[32][32];  // [lane][j]
 };
 
 static void warp_fft1024(WarpRegs& w, bool inverse, float2* tile) {
     for (int lane = 0; lane < 32; ++lane) {
-        if (inverse) wfft_phase1(w.im[lane], w.re[lane], lane, g_tw1.data(), tile);
-        else wfft_phase1(w.re[lane], w.im[lane], lane, g_tw1.data(), tile);
+        if (inverse) wfft_phase1<true>(w.x[lane], lane, g_tw1.data(), tile);
+        else wfft_phase1<false>(w.x[lane], lane, g_tw1.data(), tile);
     }
     for (int lane = 0; lane < 32; ++lane) {
-        if (inverse) wfft_phase2(w.im[lane], w.re[lane], lane, tile);
-        else wfft_phase2(w.re[lane], w.im[lane], lane, tile);
+        if (inverse) wfft_phase2<true>(w.x[lane], lane, tile);
+        else wfft_phase2<false>(w.x[lane], lane, tile);
     }
 }
 
@@ -49,13 +49,10 @@ void emu_fft1024(float2* x, int inverse) {
     std::vector<float2> tile(kTileF2);
     WarpRegs* w = new WarpRegs;
     for (int lane = 0; lane < 32; ++lane)
-        for (int j = 0; j < 32; ++j) {
-            w->re[lane][j] = x[lane + 32 * j].x;
-            w->im[lane][j] = x[lane + 32 * j].y;
-        }
+        for (int j = 0; j < 32; ++j) w->x[lane][j] = x[lane + 32 * j];
     warp_fft1024(*w, inverse != 0, tile.data());
     for (int lane = 0; lane < 32; ++lane)
-        for (int j = 0; j < 32; ++j) x[lane + 32 * j] = make_float2(w->re[lane][j], w->im[lane][j]);
+        for (int j = 0; j < 32; ++j) x[lane + 32 * j] = w->x[lane][j];
     delete w;
 }
 
@@ -111,12 +108,12 @@ void emu_cell_profile(const float2* iq, int N, int n_ms, double fs, double doppl
         for (int r = 0; r < s; ++r)
             for (int half = 0; half < 2; ++half) {
                 for (int lane = 0; lane < 32; ++lane) {
-                    load_vec(w->re[lane], w->im[lane], lane, ypoly.data() + (size_t)r * kFft);
-                    if (half) mul_tw2(w->re[lane], w->im[lane], lane, g_tw2.data());
+                    load_vec(w->x[lane], lane, ypoly.data() + (size_t)r * kFft);
+                    if (half) mul_tw2(w->x[lane], lane, g_tw2.data());
                 }
                 warp_fft1024(*w, false, tile.data());
                 float2* dst = &spec[(((size_t)i * s + r) * 2 + half) * kFft];
-                for (int lane = 0; lane < 32; ++lane) store_vec(w->re[lane], w->im[lane], lane, dst);
+                for (int lane = 0; lane < 32; ++lane) store_vec(w->x[lane], lane, dst);
             }
     }
     // ---- correlate_cells ----
@@ -133,41 +130,37 @@ void emu_cell_profile(const float2* iq, int N, int n_ms, double fs, double doppl
                 WarpRegs* ww = half ? wo : w;
                 for (int lane = 0; lane < 32; ++lane) {
                     if (kind == 1) {
-                        for (int j = 0; j < 32; ++j) ww->re[lane][j] = ww->im[lane][j] = 0.f;
+                        for (int j = 0; j < 32; ++j) ww->x[lane][j] = make_float2(0.f, 0.f);
                         for (int i = 0; i < n_ms; ++i) {
-                            float tr[32], ti[32];
-                            load_vec(tr, ti, lane, &spec[(((size_t)i * s + r) * 2 + half) * kFft]);
-                            for (int j = 0; j < 32; ++j) {
-                                ww->re[lane][j] += tr[j];
-                                ww->im[lane][j] += ti[j];
-                            }
+                            float2 t[32];
+                            load_vec(t, lane, &spec[(((size_t)i * s + r) * 2 + half) * kFft]);
+                            for (int j = 0; j < 32; ++j) ww->x[lane][j] = c_add(ww->x[lane][j], t[j]);
                         }
-                        mul_vec(ww->re[lane], ww->im[lane], lane, crep.data() + half * 1024);
+                        mul_vec(ww->x[lane], lane, crep.data() + half * 1024);
                     } else {
-                        load_mul_vec(ww->re[lane], ww->im[lane], lane, &spec[(((size_t)it * s + r) * 2 + half) * kFft],
-                                     crep.data() + half * 1024);
+                        load_mul_vec(ww->x[lane], lane, &spec[(((size_t)it * s + r) * 2 + half) * kFft], crep.data() + half * 1024);
                     }
                 }
                 warp_fft1024(*ww, true, half ? tileO.data() : tile.data());
                 // (all lanes have finished phase 2 before the tile is reused for the exchange)
                 for (int lane = 0; lane < 32; ++lane)
-                    exchange_store(ww->re[lane], ww->im[lane], lane, half, half ? tileO.data() : tile.data());
+                    exchange_store(ww->x[lane], lane, half, half ? tileO.data() : tile.data());
             }
             for (int half = 0; half < 2; ++half)
                 for (int lane = 0; lane < 32; ++lane) {
-                    float xr[16], xi[16];
-                    if (half == 0) combine_even(w->re[lane], w->im[lane], lane, g_tw2.data(), tileO.data(), xr, xi);
-                    else combine_odd(wo->re[lane], wo->im[lane], lane, g_tw2.data(), tile.data(), xr, xi);
+                    float2 o16[16];
+                    if (half == 0) combine_even(w->x[lane], lane, g_tw2.data(), tileO.data(), o16);
+                    else combine_odd(wo->x[lane], lane, g_tw2.data(), tile.data(), o16);
                     for (int jj = 0; jj < 16; ++jj) {
                         const int q = lane + 32 * (16 * half + jj);
                         const int n = s * q + r;
                         float& a = acc[((size_t)half * 32 + lane) * 16 + jj];
-                        if (kind == 2) a += gb_mag(xr[jj], xi[jj]);
+                        if (kind == 2) a += gb_mag(o16[jj]);
                         else {
-                            a = gb_mag(xr[jj], xi[jj]);
+                            a = gb_mag(o16[jj]);
                             if (q < kChips) {
-                                out[2 * n] = xr[jj];
-                                out[2 * n + 1] = xi[jj];
+                                out[2 * n] = o16[jj].x;
+                                out[2 * n + 1] = o16[jj].y;
                             }
                         }
                     }
@@ -221,22 +214,20 @@ extern "C" int emu_track_rot_ok(double mr, double mi, int fast) { return fast ? 
 extern "C" void emu_ifft2048_pruned(const float2* y_even, const float2* y_odd, float2* out /*[1024]*/) {
     init_tables();
     std::vector<float2> tile(kTile64F2);
-    static float ra[32][32], ia[32][32], rb[32][32], ib[32][32];
+    static float2 a[32][32], b[32][32];
     for (int lane = 0; lane < 32; ++lane)
         for (int j = 0; j < 32; ++j) {
-            ra[lane][j] = y_even[lane + 32 * j].x;
-            ia[lane][j] = y_even[lane + 32 * j].y;
-            rb[lane][j] = y_odd[lane + 32 * j].x;
-            ib[lane][j] = y_odd[lane + 32 * j].y;
+            a[lane][j] = y_even[lane + 32 * j];
+            b[lane][j] = y_odd[lane + 32 * j];
         }
-    for (int lane = 0; lane < 32; ++lane) {  // inverse = forward on swapped re/im
-        w2048_phase1<0>(ia[lane], ra[lane], lane, g_tw1.data(), tile.data());
-        w2048_phase1<1>(ib[lane], rb[lane], lane, g_tw1.data(), tile.data());
+    for (int lane = 0; lane < 32; ++lane) {
+        w2048_phase1<0>(a[lane], lane, g_tw1.data(), tile.data());
+        w2048_phase1<1>(b[lane], lane, g_tw1.data(), tile.data());
     }
     for (int lane = 0; lane < 32; ++lane) {
-        float re[64], im[64];
-        w2048_phase2(im, re, lane, tile.data());
-        for (int k2 = 0; k2 < 32; ++k2) out[lane + 32 * k2] = make_float2(re[k2], im[k2]);
+        float2 x[64];
+        w2048_phase2(x, lane, tile.data());
+        for (int k2 = 0; k2 < 32; ++k2) out[lane + 32 * k2] = x[k2];
     }
 }
 
