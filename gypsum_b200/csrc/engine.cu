@@ -270,14 +270,15 @@ int pick_rsplit(const gb200_engine* e, int np, long long n_cells) {
     return gcd_int(e->s, np);
 }
 
-// Single-millisecond non-coherent, record-only launches use the one-warp-per-transform kernel (12 warps per CTA at
-// 168 registers): measured -1 % (config 2), -7 % (16.368 Msps), -8 % (one block) against the warp-pair kernel.  With
-// multi-millisecond accumulators it only fits 8 warps per SM and loses 8 %, so those launches keep the pair kernel.
-// Returns the warps per CTA, or 0 for the pair kernel.  GB200_W2048=0 disables, =8 forces it for every M.
+// Non-coherent, record-only launches use the one-warp-per-transform kernel: 12 warps per CTA (168 registers) for
+// single-millisecond searches, 8 warps (the 32 accumulators live across the milliseconds: 226 registers) for longer
+// integrations.  With the packed-FP32 codelets it beats the warp-pair kernel everywhere (config 3: 0.219 -> 0.181 ms,
+// profiles/ablation_r2.md), so the pair kernel keeps only the coherent and full-profile launches.
+// Returns the warps per CTA, or 0 for the pair kernel.  GB200_W2048=0 disables it, =10 runs single-ms searches with 10 warps.
 int pick_w2048(const gb200_engine* e, int M, int kind, bool profile) {
     if (e->w2048 <= 0 || kind != GB200_NON_COHERENT || profile) return 0;
     if (M == 1) return e->w2048 == 10 ? 10 : 12;
-    return e->w2048 == 8 ? 8 : 0;
+    return 8;
 }
 
 // Warp pairs per CTA: 10 (20 warps / SM) for single-millisecond non-coherent searches, 8 otherwise (the
