@@ -34,9 +34,9 @@ __device__ __forceinline__ int pymod_int(int a, int m) {
 // The float64 loop filters run on one thread; keeping them out of line keeps the per-millisecond instruction
 // footprint of the other warps small (the loop body otherwise overflows the instruction cache).
 __device__ __noinline__ void track_update_device(TrackState* st, float2 E, float2 L, float2 peak, float strength, int key,
-                                                 double t0, double fs, TrackMsRecord* out) {
+                                                 double t0, const TrackConsts* tc, const double* rtab, TrackMsRecord* out) {
     TrackMsRecord rec;
-    track_update(*st, E, L, peak, strength, key, t0, fs, rec);
+    track_update(*st, E, L, peak, strength, key, t0, *tc, rtab, rec);
     *out = rec;
 }
 
@@ -55,6 +55,8 @@ __global__ void __launch_bounds__(kTrackThreads, 1) k_track_channels(const Track
     float2* el = reinterpret_cast<float2*>(partial + 8);              // [2] early, late
     float2* coarse = el + 2;                                          // [16] carrier at samples 0, 256, ... (+ phase)
     uint64_t* mbar = reinterpret_cast<uint64_t*>(coarse + 16);
+    double* rtab = reinterpret_cast<double*>(mbar + 2);               // [256] 1 / n for the lock-window counts
+    TrackConsts* tc = reinterpret_cast<TrackConsts*>(rtab + 256);
 
     const int slot = blockIdx.x;                                     // where this CTA's records go
     const int ch = a.channel_idx ? a.channel_idx[slot] : slot;       // which channel's state it advances
@@ -73,7 +75,11 @@ __global__ void __launch_bounds__(kTrackThreads, 1) k_track_channels(const Track
             if (shd) shd[i] = v;
         }
     }
-    if (tid == 0) mbar_init(mbar, 1);
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        *tc = track_consts(a.fs);
+    }
+    rtab[tid] = tid ? 1.0 / static_cast<double>(tid) : 0.0;  // kTrackThreads == 256 entries
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(mbar, 4 * kFft * sizeof(float2));
@@ -136,25 +142,18 @@ __global__ void __launch_bounds__(kTrackThreads, 1) k_track_channels(const Track
 
         if (warp < n_fft_warps) {
             float2 x[32];
-            // forward transform, spectrum product, inverse transform (= conj, forward, conj): one copy of the
-            // warp-FFT code serves both passes.
-#pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-                if (pass == 0) {
-                    build_z(x, lane, r, S, ypoly);
-                    if (h) mul_tw2(x, lane, tw2_s);
-                } else {
-                    mul_vec(x, lane, crep_s + h * kFft);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j].y = -x[j].y;
-                }
-                wfft_phase1<false>(x, lane, tw1_s, tile);
-                __syncwarp();
-                wfft_phase2<false>(x, lane, tile);
-                __syncwarp();
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j].y = -x[j].y;
+            // forward transform, spectrum product, inverse transform
+            build_z(x, lane, r, S, ypoly);
+            if (h) mul_tw2(x, lane, tw2_s);
+            wfft_phase1<false>(x, lane, tw1_s, tile);
+            __syncwarp();
+            wfft_phase2<false>(x, lane, tile);
+            __syncwarp();
+            mul_vec(x, lane, crep_s + h * kFft);
+            wfft_phase1<true>(x, lane, tw1_s, tile);
+            __syncwarp();
+            wfft_phase2<true>(x, lane, tile);
+            __syncwarp();
             exchange_store(x, lane, h, tile);
             pair_barrier(r);
             float2 out16[16];
@@ -230,7 +229,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) k_track_channels(const Track
             }
             const double m = static_cast<double>(mx);
             const float strength = static_cast<float>(m / ((sum - cnt * m) / (a.N - cnt)));  // utils.py:111-116
-            track_update_device(st, el[0], el[1], make_float2(pre, pim), strength, key, t0, a.fs, &out[k]);
+            track_update_device(st, el[0], el[1], make_float2(pre, pim), strength, key, t0, tc, rtab, &out[k]);
         }
         // the __syncthreads at the top of the next millisecond publishes st / frees el, partial
     }
@@ -245,7 +244,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) k_track_channels(const Track
 size_t track_smem_bytes(int N, int s) {
     return (2 * static_cast<size_t>(N) + static_cast<size_t>(s) * kFft + 4 * kFft + 2 * static_cast<size_t>(s) * kTileF2) *
                sizeof(float2) +
-           sizeof(TrackState) + 8 * sizeof(TrackPartial) + (2 + 16) * sizeof(float2) + 16;
+           sizeof(TrackState) + 8 * sizeof(TrackPartial) + (2 + 16) * sizeof(float2) + 16 + 256 * sizeof(double) + sizeof(TrackConsts);
 }
 
 cudaError_t configure_track_kernel() {

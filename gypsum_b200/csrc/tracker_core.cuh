@@ -56,6 +56,18 @@ GB_HD GB_INLINE double pymod(double a, double m) {  // Python's float % for m > 
     if (r < 0.0) r += m;
     return r;
 }
+// The same value as pymod() without the fmod call when a lies in [-m, 2m) -- where a loop state that moved by one small
+// step from [0, m) always lies: a - m is exact there (Sterbenz) and equals fmod(a, m); a + m for a negative a is exactly
+// what Python's float % computes (fmod(a, m) = a, then + m).
+GB_HD GB_INLINE double pymod_near(double a, double m) {
+    if (a >= 0.0) {
+        if (a < m) return a;
+        if (a < 2.0 * m) return a - m;
+    } else if (a >= -m) {
+        return a + m;
+    }
+    return pymod(a, m);
+}
 GB_HD GB_INLINE double sign_of(double x) { return x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : 0.0); }
 
 GB_HD inline void track_state_init(TrackState& st, int prn, double doppler, double carrier_phase, int code_phase) {
@@ -81,38 +93,100 @@ GB_HD inline bool track_rot_ok(double mr, double mi) {
     return centered < 6.0;
 }
 // The same decision without the atan2 / fmod chain on almost every millisecond: |mi| against tan(6 deg) |mr| with a guard
-// band of +-0.01 degree, inside which -- and for NaNs and the origin -- the reference arithmetic above decides.
-// Equivalence is tested on the host over 36 k directions (tests/test_tracker_cpu.py); on B200 it takes 32 channels x 60 s
-// from 0.448 s to 0.423 s (profiles/ablation_r2.md).
-GB_HD inline bool track_rot_ok_fast(double mr, double mi) {
+// band of +-0.01 degree.  1 / 0 = decided, -1 = inside the band (or NaN / the origin): the reference arithmetic above decides.
+GB_HD inline int track_rot_quick(double mr, double mi) {
     const double a = fabs(mi), b = fabs(mr);
-    if (a < 0.10492777752783379 * b) return true;   // tan(5.99 deg)
-    if (a > 0.10528069947757225 * b) return false;  // tan(6.01 deg)
-    return track_rot_ok(mr, mi);
+    if (a < 0.10492777752783379 * b) return 1;   // tan(5.99 deg)
+    if (a > 0.10528069947757225 * b) return 0;   // tan(6.01 deg)
+    return -1;
+}
+// Equivalence with track_rot_ok is tested on the host over 36 k directions (tests/test_tracker_cpu.py).
+GB_HD inline bool track_rot_ok_fast(double mr, double mi) {
+    const int q = track_rot_quick(mr, mi);
+    return q >= 0 ? q != 0 : track_rot_ok(mr, mi);
 }
 
+// What _calculate_loop_filter_alpha_and_beta (tracker.py:228-244; lru-cached there as well) returns for the two loop
+// bandwidths the tracker ever uses: [0] = 3 Hz (locked), [1] = 6 Hz (pull-in).  Same expressions, same evaluation order.
+struct TrackConsts {
+    double alpha[2], beta[2];
+};
+GB_HD inline TrackConsts track_consts(double fs) {
+    TrackConsts c;
+    const double ts = 1.0 / fs;
+    for (int i = 0; i < 2; ++i) {
+        const double bw = i == 0 ? 3.0 : 6.0;
+        c.alpha[i] = 4.0 * (1.0 / sqrt(2.0)) * bw * ts;
+        c.beta[i] = 4.0 * (bw * bw) * ts;
+    }
+    return c;
+}
+
+// 1 / n for the window counts 1..250: from a table when the caller has one (the kernel keeps it in shared memory), else
+// computed.  Only ever used inside guard bands (below), never for a value that is handed out.
+GB_HD GB_INLINE double recip_count(const double* rtab, int n) { return rtab ? rtab[n] : 1.0 / n; }
+
 // tracker.py:157-203.  Called after the current peak was pushed and before the current error is.
-GB_HD inline bool track_is_locked(const TrackState& st) {
+// The reference forms five means / variances with divisions every millisecond and compares them with fixed thresholds.
+// Here each quantity is first formed with a reciprocal multiply (a few ulp off at most); only if it lands within a guard
+// band of its threshold -- 1e-9 relative to the magnitudes it was subtracted from, seven orders above any possible
+// difference -- is it recomputed with the reference's divisions.  The decisions are therefore the reference's, always; the
+// divisions, the atan2 and the fmod run on a vanishing fraction of the milliseconds.  The three tests are independent and
+// side-effect free, so a failed one ends the evaluation.
+GB_HD inline bool track_is_locked(const TrackState& st, const double* rtab = nullptr) {
     if (st.err_count < kLockWindow) return false;
-    const double mean = st.e_s1 / kLockWindow;
-    const double var = st.e_s2 / kLockWindow - mean * mean;  // np.var (population)
-    const bool var_ok = var < 900.0;                         // config.py:27
-    bool i_ok = true, rot_ok = true;
+    {
+        const double r = 1.0 / kLockWindow;  // compile-time constant
+        double mean = st.e_s1 * r;
+        const double a = st.e_s2 * r;
+        double var = a - mean * mean;  // np.var (population)
+        if (!(fabs(var - 900.0) > 1e-9 * (a + 900.0))) {
+            mean = st.e_s1 / kLockWindow;
+            var = st.e_s2 / kLockWindow - mean * mean;
+        }
+        if (!(var < 900.0)) return false;  // config.py:27
+    }
     if (st.peak_count > 2) {
-        double nv = 0.0, pv = 0.0, mr = 0.0, mi = 0.0;
+        double nv = 0.0, pv = 0.0, mr = 0.0, mi = 0.0, scale = 2.0;
+        if (st.n_cnt >= 2) {
+            const double rn = recip_count(rtab, st.n_cnt);
+            mr = st.n_sre * rn;
+            mi = st.n_sim * rn;
+            const double a = st.n_sre2 * rn;
+            nv = a - mr * mr;
+            scale += a;
+        }
+        if (st.p_cnt >= 2) {
+            const double rp = recip_count(rtab, st.p_cnt);
+            const double pm = st.p_sre * rp, a = st.p_sre2 * rp;
+            pv = a - pm * pm;
+            scale += a;
+        }
+        double x = (nv + pv) / 2.0;
+        if (!(fabs(x - 2.0) > 1e-9 * scale)) {
+            nv = pv = 0.0;
+            if (st.n_cnt >= 2) {
+                const double m = st.n_sre / st.n_cnt;
+                nv = st.n_sre2 / st.n_cnt - m * m;
+            }
+            if (st.p_cnt >= 2) {
+                const double pm = st.p_sre / st.p_cnt;
+                pv = st.p_sre2 / st.p_cnt - pm * pm;
+            }
+            x = (nv + pv) / 2.0;
+        }
+        if (!(x < 2.0)) return false;
+        // 6-degree test: outside +-0.01 degree of the boundary the reciprocal-multiply means decide (their error is 1e-16
+        // relative); inside, the reference's divisions, atan2 and modulo do
+        const int q = track_rot_quick(mr, mi);
+        if (q >= 0) return q != 0;
         if (st.n_cnt >= 2) {
             mr = st.n_sre / st.n_cnt;
             mi = st.n_sim / st.n_cnt;
-            nv = st.n_sre2 / st.n_cnt - mr * mr;
         }
-        if (st.p_cnt >= 2) {
-            const double pm = st.p_sre / st.p_cnt;
-            pv = st.p_sre2 / st.p_cnt - pm * pm;
-        }
-        i_ok = (nv + pv) / 2.0 < 2.0;
-        rot_ok = track_rot_ok_fast(mr, mi);
+        return track_rot_ok(mr, mi);
     }
-    return var_ok && i_ok && rot_ok;
+    return true;
 }
 
 GB_HD inline void track_push_peak(TrackState& st, double re, double im) {
@@ -204,25 +278,22 @@ GB_HD inline bool track_constellation(const TrackState& st, double& circularity,
 // The scalar part of GpsSatelliteTracker.process_samples for one millisecond.  E, L, peak come from the
 // correlators (float32); everything after is float64.
 GB_HD inline void track_update(TrackState& st, float2 E, float2 L, float2 peak, float strength, int peak_offset,
-                               double start_time, double fs, TrackMsRecord& out) {
+                               double start_time, const TrackConsts& tc, const double* rtab, TrackMsRecord& out) {
     // --- DLL, tracker.py:297-303 ---
     const double er = E.x, ei = E.y, lr = L.x, li = L.y;
     const double disc = ((er * er + ei * ei) - (lr * lr + li * li)) / 2.0;
     st.phase_acc += disc * 0.002;
     st.code_phase = static_cast<int>(st.phase_acc);  // int(): truncation toward zero
-    st.phase_acc = pymod(st.phase_acc, 2046.0);      // hard-wired 2046 in the reference
+    st.phase_acc = pymod_near(st.phase_acc, 2046.0);  // hard-wired 2046 in the reference
     // --- histories, tracker.py:346 ---
     const double pre = peak.x, pim = peak.y;
     track_push_peak(st, pre, pim);
     // --- PLL, tracker.py:246-262 ---
     const double error = pre * pim;
-    const bool locked = track_is_locked(st);
-    const double bw = locked ? 3.0 : 6.0;
-    const double ts = 1.0 / fs;
-    const double alpha = 4.0 * (1.0 / sqrt(2.0)) * bw * ts;
-    const double beta = 4.0 * (bw * bw) * ts;
+    const bool locked = track_is_locked(st, rtab);
+    const double alpha = tc.alpha[locked ? 0 : 1], beta = tc.beta[locked ? 0 : 1];  // 3 Hz when locked, 6 Hz to pull in
     st.carrier_phase += error * alpha;
-    st.carrier_phase = pymod(st.carrier_phase, kTau);
+    st.carrier_phase = pymod_near(st.carrier_phase, kTau);
     st.doppler += error * beta;
     track_push_error(st, error);
     out.doppler_hist = st.doppler;  // tracker.py:352-353: appended to the histories before the check below

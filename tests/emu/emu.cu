@@ -203,8 +203,9 @@ void emu_track_init(TrackState* st, int prn, double doppler, double carrier_phas
 }
 void emu_track_update(TrackState* st, const float* elp /* E.re E.im L.re L.im P.re P.im */, float strength, int off,
                       double t0, double fs, TrackMsRecord* out) {
+    const TrackConsts tc = track_consts(fs);
     track_update(*st, make_float2(elp[0], elp[1]), make_float2(elp[2], elp[3]), make_float2(elp[4], elp[5]), strength, off,
-                 t0, fs, *out);
+                 t0, tc, nullptr, *out);
 }
 }
 
