@@ -97,15 +97,27 @@ __global__ void __launch_bounds__(spec_warps(S) * 32, S == 2 ? 5 : 1) k_doppler_
     // Carrier exp(-j 2 pi f (n + i N)/fs) (utils.py:93-96) as coarse[n / 256] * fine[n % 256]: both factors get an
     // exact float64-reduced phase, so there is one sincos per thread instead of one per sample and no recurrence
     // error growth.
-    const int n_coarse = (a.N + kSpecThreads - 1) / kSpecThreads;
-    if (tid < n_coarse) coarse[tid] = carrier_at(f, static_cast<double>(tid * kSpecThreads + i * a.N), a.inv_fs);
+    constexpr int kIter = (kChips * S + kSpecThreads - 1) / kSpecThreads;  // samples per thread (16 for every S but 16: 64)
+    // coalesced float2 loads of the 1-ms IQ vector, ALL issued before the carrier set-up and the first use (the loop form
+    // stalled on every load: 25 % of the kernel's stall samples, profiles/ablation_r2.md)
+    constexpr int kBatch = kIter < 16 ? kIter : 16;
+    float2 v[kBatch];
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k) {
+        const int n = tid + k * kSpecThreads;
+        v[k] = n < kChips * S ? src[n] : make_float2(0.f, 0.f);
+    }
+    if (tid < kIter) coarse[tid] = carrier_at(f, static_cast<double>(tid * kSpecThreads + i * a.N), a.inv_fs);
     const float2 fine = carrier_at(f, static_cast<double>(tid), a.inv_fs);
     __syncthreads();
-    // coalesced float2 loads of the 1-ms IQ vector; wipe-off; de-interleave by polyphase branch
-    for (int k = 0, n = tid; n < a.N; ++k, n += kSpecThreads) {
-        const float2 y = cmul(src[n], cmul(coarse[k], fine));
-        ypoly[(n % S) * kFft + zpos(n / S)] = y;
+    // wipe-off; de-interleave by polyphase branch
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k) {
+        const int n = tid + k * kSpecThreads;
+        if (n < kChips * S) ypoly[(n % S) * kFft + zpos(n / S)] = cmul(v[k], cmul(coarse[k], fine));
     }
+    for (int k = kBatch, n = tid + kBatch * kSpecThreads; n < a.N; ++k, n += kSpecThreads)
+        ypoly[(n % S) * kFft + zpos(n / S)] = cmul(src[n], cmul(coarse[k], fine));
     __syncthreads();
     if (tid < S) ypoly[tid * kFft + zpos(kFft - 1)] = ypoly[tid * kFft + zpos(0)];
     __syncthreads();
