@@ -57,6 +57,7 @@ SYMBOLS = {
     "gb200_acquire_cells": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P]),
     "gb200_detect": (C.c_int, [_P, C.c_int, _P, C.c_int, _P]),
     "gb200_correlation_profile": (C.c_int, [_P, C.c_int, C.c_double, C.c_int, C.c_int, _P]),
+    "gb200_correlation_profile_replica": (C.c_int, [_P, _P, C.c_double, C.c_int, C.c_int, _P]),
     "gb200_tracker_create": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.POINTER(_P)]),
     "gb200_tracker_destroy": (C.c_int, [_P]),
     "gb200_tracker_process": (C.c_int, [_P, C.c_int, _P, _P, _P]),
@@ -296,6 +297,19 @@ class Engine:
         self._check(
             self._lib.gb200_correlation_profile(self._h, int(prn_idx), float(doppler_hz), int(n_ms), int(kind), _ptr(out)),
             "gb200_correlation_profile",
+        )
+        return out.view(np.complex64) if kind == COHERENT else out
+
+    def correlation_profile_replica(self, replica: np.ndarray, doppler_hz: float, n_ms: int, kind: int) -> np.ndarray:
+        """utils.py:77-108 against an ARBITRARY complex replica of samples_per_ms samples (direct evaluation)."""
+        n = self.samples_per_ms
+        rep = np.ascontiguousarray(replica, dtype=np.complex64)
+        if rep.shape != (n,):
+            raise ValueError(f"replica must have {n} samples")
+        out = np.empty(n * (2 if kind == COHERENT else 1), dtype=np.float32)
+        self._check(
+            self._lib.gb200_correlation_profile_replica(self._h, _ptr(rep), float(doppler_hz), int(n_ms), int(kind), _ptr(out)),
+            "gb200_correlation_profile_replica",
         )
         return out.view(np.complex64) if kind == COHERENT else out
 

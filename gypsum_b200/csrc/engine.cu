@@ -74,7 +74,7 @@ int env_int(const char* name, int dflt) {
 struct gb200_engine {
     int device = 0, fs = 0, N = 0, s = 0, num_sms = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    DevBuf<float2> tw1, tw2, crep, iq_own, spec;
+    DevBuf<float2> tw1, tw2, crep, iq_own, spec, d_replica;
     DevBuf<uint8_t> chips;
     DevBuf<double> d_doppler;
     DevBuf<int> d_ints;
@@ -131,6 +131,7 @@ struct gb200_engine {
         tw1.release();
         tw2.release();
         crep.release();
+        d_replica.release();
         iq_own.release();
         spec.release();
         chips.release();
@@ -975,6 +976,33 @@ int gb200_correlation_profile(gb200_engine* e, int prn, double dop, int n_ms, in
     const int32_t p = prn;
     int rc = run_cells(e, 1, &p, &dop, nullptr, n_ms, kind, e->d_records.p, e->d_profile.p);
     if (rc) return rc;
+    GB_CUDA(e, cudaMemcpyAsync(e->h_profile.p, e->d_profile.p, nf * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    GB_CUDA(e, cudaStreamSynchronize(e->stream));
+    memcpy(out_host, e->h_profile.p, nf * sizeof(float));
+    return GB200_OK;
+}
+
+int gb200_correlation_profile_replica(gb200_engine* e, const float* replica_host, double dop, int n_ms, int kind,
+                                      float* out_host) {
+    if (!e) return GB200_EINVAL;
+    if (!replica_host || !out_host) GB_FAIL(e, GB200_EINVAL, "null buffer");
+    if (kind != GB200_COHERENT && kind != GB200_NON_COHERENT) GB_FAIL(e, GB200_EINVAL, "Unexpected integration type");
+    if (!e->iq) GB_FAIL(e, GB200_ESTATE, "no IQ loaded (gb200_upload_iq / gb200_bind_iq_device)");
+    if (n_ms < 1) GB_FAIL(e, GB200_EINVAL, "need at least one whole millisecond of samples");
+    if (static_cast<int64_t>(n_ms) * e->N > e->iq_samples)
+        GB_FAIL(e, GB200_EINVAL, "need %lld samples, %lld loaded", static_cast<long long>(n_ms) * e->N,
+                static_cast<long long>(e->iq_samples));
+    GB_CUDA(e, cudaSetDevice(e->device));
+    const size_t nf = static_cast<size_t>(e->N) * (kind == GB200_COHERENT ? 2 : 1);
+    GB_CUDA(e, cudaStreamSynchronize(e->stream));  // staging buffers may still be in flight
+    GB_CUDA(e, e->d_profile.ensure(nf));
+    GB_CUDA(e, e->h_profile.ensure(std::max(nf, static_cast<size_t>(2) * e->N)));
+    GB_CUDA(e, e->d_replica.ensure(e->N));
+    memcpy(e->h_profile.p, replica_host, sizeof(float2) * e->N);  // the pinned profile buffer doubles as replica staging
+    GB_CUDA(e, cudaMemcpyAsync(e->d_replica.p, e->h_profile.p, sizeof(float2) * e->N, cudaMemcpyHostToDevice, e->stream));
+    GB_CUDA(e, launch_correlate_generic(e->iq, e->d_replica.p, e->N, n_ms, dop, 1.0 / static_cast<double>(e->fs), kind,
+                                        e->d_profile.p, e->stream));
+    e->launches++;
     GB_CUDA(e, cudaMemcpyAsync(e->h_profile.p, e->d_profile.p, nf * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     GB_CUDA(e, cudaStreamSynchronize(e->stream));
     memcpy(out_host, e->h_profile.p, nf * sizeof(float));

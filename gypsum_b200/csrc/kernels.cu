@@ -585,6 +585,60 @@ __global__ void __launch_bounds__(NW * 32, 1) k_correlate_w2048(const CorrelateA
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Generic replica (utils.py:59-73 with ANY length-N complex prn_replica, not only chips repeated N/1023 times): the circular
+// cross-correlation out[k] = sum_n y[n] conj(p[(n - k) mod N]) evaluated directly, float64 accumulation, one thread per lag.
+// Not a hot path -- the receiver only ever passes its own replicas, which take the FFT kernels -- but the public helpers
+// accept whatever the reference's do.  N^2 complex multiply-adds: 4.2 M at 2.046 Msps, 268 M at 16.368 Msps.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kGenericThreads = 128, kGenericChunk = 1024;
+__global__ void __launch_bounds__(kGenericThreads) k_correlate_generic(const float2* iq, const float2* replica, int N, int n_ms,
+                                                                        double doppler, double inv_fs, int kind, float* out) {
+    __shared__ float2 ys[kGenericChunk];
+    const int k = blockIdx.x * kGenericThreads + threadIdx.x;  // lag
+    double acc_re = 0.0, acc_im = 0.0, acc_abs = 0.0;
+    for (int i = 0; i < n_ms; ++i) {
+        double cr = 0.0, ci = 0.0;
+        for (int n0 = 0; n0 < N; n0 += kGenericChunk) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < kGenericChunk && n0 + t < N; t += kGenericThreads) {
+                const int n = n0 + t;
+                // utils.py:93-97: exp(-j tau f (n + i N) / fs), phase reduced in float64 like every other kernel
+                ys[t] = wipeoff(iq[static_cast<size_t>(i) * N + n], doppler * ((static_cast<double>(n) + static_cast<double>(i) * N) * inv_fs));
+            }
+            __syncthreads();
+            if (k < N) {
+                const int lim = min(kGenericChunk, N - n0);
+                int idx = n0 - k;
+                idx = idx < 0 ? idx + N : idx;  // (n - k) mod N for the chunk's first sample
+                for (int t = 0; t < lim; ++t) {
+                    const float2 y = ys[t], p = replica[idx];
+                    cr += static_cast<double>(y.x) * p.x + static_cast<double>(y.y) * p.y;   // y * conj(p)
+                    ci += static_cast<double>(y.y) * p.x - static_cast<double>(y.x) * p.y;
+                    idx = idx + 1 == N ? 0 : idx + 1;
+                }
+            }
+        }
+        acc_re += cr;                           // utils.py:102
+        acc_im += ci;
+        acc_abs += sqrt(cr * cr + ci * ci);     // utils.py:104
+    }
+    if (k < N) {
+        if (kind == kKindCoherent) {
+            out[2 * k] = static_cast<float>(acc_re);
+            out[2 * k + 1] = static_cast<float>(acc_im);
+        } else {
+            out[k] = static_cast<float>(acc_abs);
+        }
+    }
+}
+cudaError_t launch_correlate_generic(const float2* iq, const float2* replica, int N, int n_ms, double doppler, double inv_fs,
+                                     int kind, float* out, cudaStream_t st) {
+    k_correlate_generic<<<(N + kGenericThreads - 1) / kGenericThreads, kGenericThreads, 0, st>>>(iq, replica, N, n_ms, doppler,
+                                                                                                  inv_fs, kind, out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // On-device Doppler refinement: the control flow of acquisition.py:70-152 without host round trips.  The
 // correlation work of every pass still runs in doppler_spectra / correlate_cells; these kernels only plan the
 // next pass's bins and apply the reference's selection rules.

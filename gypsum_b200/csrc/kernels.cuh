@@ -136,6 +136,8 @@ cudaError_t launch_replica_spectra(const uint8_t* chips_dev, int n_prn, float2* 
 cudaError_t launch_doppler_spectra(const SpectraArgs& a, cudaStream_t st);
 cudaError_t launch_correlate_cells(const CorrelateArgs& a, int np, int grid, cudaStream_t st);
 cudaError_t launch_correlate_w2048(const CorrelateArgs& a, int nw, int grid, cudaStream_t st);
+cudaError_t launch_correlate_generic(const float2* iq, const float2* replica, int N, int n_ms, double doppler, double inv_fs,
+                                     int kind, float* out, cudaStream_t st);
 cudaError_t configure_kernels();
 
 }  // namespace gb

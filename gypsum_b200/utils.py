@@ -72,32 +72,44 @@ class _EnginePool:
 POOL = _EnginePool()
 
 
+class NotAChipReplica(ValueError):
+    """The replica is not chips repeated N/1023 times: the FFT kernels cannot take it, the direct kernel can."""
+
+
 def chips_of_replica(prn_as_complex: np.ndarray, n: int) -> tuple[np.ndarray, int]:
     """Recover (chips uint8[1023], roll) from a replica of the reference's form
-    roll(repeat(+-1 chips, s), roll) (satellite.py:20-31; tracker.py:286 rolls it).  Anything else is rejected."""
+    roll(repeat(+-1 chips, s), roll) (satellite.py:20-31; tracker.py:286 rolls it).  Anything else raises NotAChipReplica
+    (a ValueError): the detector and tracker reject it, the public helpers below fall back to the generic kernel."""
     x = np.asarray(prn_as_complex)
     if x.shape != (n,):
         raise ValueError(f"replica must have {n} samples")
     s = n // 1023
     xr = np.real(x)
     if np.any(np.imag(x) != 0) or np.any(np.abs(xr) != 1):
-        raise ValueError("replica must be a +-1 chip sequence (GpsSatellite.prn_as_complex)")
+        raise NotAChipReplica("replica must be a +-1 chip sequence (GpsSatellite.prn_as_complex)")
     for p in range(s):
         y = np.roll(xr, -p)
         c = y[::s]
         if np.array_equal(np.repeat(c, s), y):
             return (c > 0).astype(np.uint8), p
-    raise ValueError("replica is not chips repeated samples_per_ms/1023 times")
+    raise NotAChipReplica("replica is not chips repeated samples_per_ms/1023 times")
 
 
 def frequency_domain_correlation(antenna_samples: np.ndarray, prn_replica: np.ndarray) -> np.ndarray:
     """utils.py:59-73: circular cross-correlation ifft(fft(x) conj(fft(prn))) of one millisecond -> complex128[N]."""
     x = np.ascontiguousarray(antenna_samples, dtype=np.complex64)
     n = x.size
-    chips, roll = chips_of_replica(prn_replica, n)
+    rep = np.asarray(prn_replica)
+    if rep.shape != (n,):
+        raise ValueError(f"replica must have {n} samples")
     ent = POOL.get(n * 1000, n)
-    idx = POOL.replica_index(ent, chips)
     eng = ent["engine"]
+    try:
+        chips, roll = chips_of_replica(rep, n)
+    except NotAChipReplica:  # any other replica: direct circular correlation on the device
+        eng.upload_iq(x)
+        return eng.correlation_profile_replica(rep, 0.0, 1, _native.COHERENT).astype(np.complex128)
+    idx = POOL.replica_index(ent, chips)
     eng.upload_iq(x)
     prof = eng.correlation_profile(idx, 0.0, 1, _native.COHERENT).astype(np.complex128)
     return np.roll(prof, -roll) if roll else prof
@@ -114,13 +126,20 @@ def integrate_correlation_with_doppler_shifted_prn(
     n_ms = data.size // n  # utils.py:34-38: a trailing partial chunk is dropped
     if n_ms == 0:
         return np.zeros(n, dtype=complex if kind == _native.COHERENT else np.float64)
-    chips, roll = chips_of_replica(prn_as_complex, n)
+    rep = np.asarray(prn_as_complex)
+    if rep.shape != (n,):
+        raise ValueError(f"replica must have {n} samples")
     ent = POOL.get(fs, n)
-    idx = POOL.replica_index(ent, chips)
     eng = ent["engine"]
+    wide = np.complex128 if kind == _native.COHERENT else np.float64
+    try:
+        chips, roll = chips_of_replica(rep, n)
+    except NotAChipReplica:  # any other replica: direct circular correlation on the device
+        eng.upload_iq(data[: n_ms * n])
+        return eng.correlation_profile_replica(rep, float(doppler_shift), n_ms, kind).astype(wide)
+    idx = POOL.replica_index(ent, chips)
     eng.upload_iq(data[: n_ms * n])
-    prof = eng.correlation_profile(idx, float(doppler_shift), n_ms, kind)
-    prof = prof.astype(np.complex128 if kind == _native.COHERENT else np.float64)
+    prof = eng.correlation_profile(idx, float(doppler_shift), n_ms, kind).astype(wide)
     return np.roll(prof, -roll) if roll else prof
 
 

@@ -139,6 +139,12 @@ int gb200_detect(gb200_engine* e, int n_sv, const int32_t* prn_idx, int n_ms, gb
  * 2N floats (coherent, interleaved re,im).                                                          */
 int gb200_correlation_profile(gb200_engine* e, int prn_idx, double doppler_hz, int n_ms, int integration_type,
                               float* out_host);
+/* The same for ANY replica (utils.py:59-73 / :77-108 accept an arbitrary complex prn_replica of N samples, not only the
+ * chips-repeated form GpsSatellite.prn_as_complex produces): replica_host is complex64[N]; the circular correlation is
+ * evaluated directly (N^2 multiply-adds, float64 accumulation).  Slow path for the public helpers, never used by the
+ * receiver's own calls.                                                                                              */
+int gb200_correlation_profile_replica(gb200_engine* e, const float* replica_host, double doppler_hz, int n_ms,
+                                      int integration_type, float* out_host);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Tracking (gypsum/tracker.py).  A tracker is a bank of channels sharing the engine's loaded IQ stream; every

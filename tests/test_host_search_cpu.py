@@ -45,6 +45,11 @@ class OracleEngine:
         prof = self._profile(prn, dop, n_ms, kind)
         return prof if kind == _native.COHERENT else np.abs(prof)
 
+    def correlation_profile_replica(self, replica, dop, n_ms, kind):
+        which = o.COHERENT if kind == _native.COHERENT else o.NON_COHERENT
+        self.generic_calls = getattr(self, "generic_calls", 0) + 1
+        return o.integrate(which, self.x[: n_ms * self.n], self.fs, self.n, float(dop), np.asarray(replica, dtype=complex))
+
 
 class Attrs:
     samples_per_second, samples_per_prn_transmission = 2046000, 2046
@@ -120,5 +125,16 @@ def test_drop_in_utils_wrappers_argument_handling(monkeypatch):
     assert np.abs(one - o.correlate_1ms(x[:n].astype(np.complex128), np.roll(rep, 6))).max() <= 1e-9 * np.abs(one).max()
     with pytest.raises(ValueError, match="Unexpected integration type"):
         integrate_correlation_with_doppler_shifted_prn("coherent", x, A, 0.0, rep)
+    # a replica that is NOT chips repeated N/1023 times goes to the generic (direct-correlation) entry point, like any
+    # array the reference's function would accept (utils.py:59-73): scaled, complex, arbitrary
+    rng = np.random.default_rng(0)
+    odd = (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    for r in (rep * 0.5, odd):
+        want = o.integrate(o.COHERENT, x, fs, n, 0.0, r)
+        got = integrate_correlation_with_doppler_shifted_prn(IntegrationType.Coherent, x, A, 0.0, r)
+        assert got.dtype == np.complex128 and np.abs(got - want).max() <= 1e-6 * np.abs(want).max()
+    one = frequency_domain_correlation(x[:n], odd)
+    assert np.abs(one - o.correlate_1ms(x[:n].astype(np.complex128), odd)).max() <= 1e-6 * np.abs(one).max()
+    assert eng.generic_calls == 3
     with pytest.raises(ValueError):
-        integrate_correlation_with_doppler_shifted_prn(IntegrationType.Coherent, x, A, 0.0, rep * 0.5)  # not +-1 chips
+        integrate_correlation_with_doppler_shifted_prn(IntegrationType.Coherent, x, A, 0.0, rep[:-1])  # wrong length
