@@ -6,8 +6,8 @@ per other BASELINE configuration.
     python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm (numpy) on the host cores
 
 One STEP = one pass of the hot path over one batch of synthetic input: `calls_per_step` x `blocks_per_call` independent
-1-ms IQ blocks @ 2.046 Msps (default 64 x 32 = 2048 blocks, 4.2 Msamples, ~22 ms of GPU work), each searched over the full
-32 PRN x 41 Doppler (+-10 kHz / 500 Hz) grid with 1 ms of non-coherent integration -- i.e. 2048 x (BASELINE config 2).
+1-ms IQ blocks @ 2.046 Msps (default 96 x 32 = 3072 blocks, 6.3 Msamples, ~27 ms of GPU work), each searched over the full
+32 PRN x 41 Doppler (+-10 kHz / 500 Hz) grid with 1 ms of non-coherent integration -- i.e. 3072 x (BASELINE config 2).
 The metric is per input sample, so the batch only sets how much work one step carries.
 
   value : steps timed with CUDA events on the launching stream, inputs already in HBM (an IQ ring larger than L2, fresh
@@ -15,8 +15,9 @@ The metric is per input sample, so the batch only sets how much work one step ca
   e2e   : the same steps through the public host API, copies inside the timed region.
           N = 1: pinned host IQ -> GridStream.submit / collect (pipelined copies) -> per-cell records in host memory.
           N > 1: ALL the step's IQ starts in rank 0's host memory and ALL per-cell records end there:
-                 ShardedBlockSearch = one H2D on rank 0, one NCCL scatter of block shares, the grid on every rank, one NCCL
-                 gather of the records, one D2H on rank 0 (north_star's "single broadcast ... final gather").
+                 ShardedBlockStream = one H2D on rank 0, one NCCL scatter of block shares, the grid on every rank, one NCCL
+                 gather of the records, one D2H on rank 0 (north_star's "single broadcast ... final gather"), two steps in
+                 flight so that rank 0's copies run under the kernels; the one-call (unpipelined) figure is reported beside it.
   N > 1 : one process per GPU (torchrun); `value` = every rank searching its own resident blocks (weak scaling, no
           data-path collective); time = max over ranks.
   configs: config3 / config4 / config5 sub-objects (N = 1), and at N > 1 config5 as a STRONG-scaling job (1000 blocks
@@ -608,19 +609,52 @@ def multi_gpu_e2e(g, eng, args, prn, dop) -> dict:
             else:
                 assert (r["doppler"][total_blocks - 1, 24], r["code_phase"][total_blocks - 1, 24]) == (1500.0, 777)
         out[key] = {"value": total_blocks * N / sec / 1e6, "seconds_per_step": sec, "steps": steps, **search.last_bytes}
-    pc = out["per_cell"]
-    return {"value": pc["value"], "unit": "Msamples/s", "h2d_bytes_per_step": pc["h2d"], "d2h_bytes_per_step": pc["d2h"],
-            "nccl_scatter_bytes_per_step": pc["scatter"], "nccl_gather_bytes_per_step": pc["gather"],
-            "blocks_per_step": total_blocks, "seconds_per_step": pc["seconds_per_step"],
-            "api": "ShardedBlockSearch.acquire_blocks: rank-0 pinned host IQ -> H2D -> NCCL scatter -> grid on every rank -> NCCL gather -> D2H -> rank-0 host records",
-            "with_on_device_best_bin_reduction": {"value": out["best_bin"]["value"], "seconds_per_step": out["best_bin"]["seconds_per_step"],
+    # the same steps as a pipelined stream: two steps in flight, rank 0's copies on the copy engines under the kernels
+    from gypsum_b200.distributed import ShardedBlockStream
+
+    for key, mode in (("per_cell_stream", None), ("best_bin_stream", "best")):
+        st = ShardedBlockStream(eng, torch.device("cuda", g.local_rank), total_blocks, N_MS, prn, dop, _native.NON_COHERENT, reduce=mode)
+        last = [None]
+
+        def sstep(k: int) -> None:
+            if st.in_flight == 2:
+                last[0] = st.collect()
+            st.submit(host)
+
+        def sdrain() -> None:
+            while st.in_flight:
+                last[0] = st.collect()
+
+        sstep(0)
+        sdrain()
+        steps = max(4, min(args.steps, 12))
+        sec = g.wall(sstep, steps, first=1, drain=sdrain) / steps
+        if g.rank == 0:
+            r = last[0]
+            if mode is None:
+                for b in (0, total_blocks // 2, total_blocks - 1):
+                    assert int(r["argmax"][b, 24, int(np.argmax(r["peak"][b, 24]))]) == 777
+            else:
+                assert (r["doppler"][total_blocks - 1, 24], r["code_phase"][total_blocks - 1, 24]) == (1500.0, 777)
+        out[key] = {"value": total_blocks * N / sec / 1e6, "seconds_per_step": sec, "steps": steps, **st.bytes_per_job}
+        del st
+    ps, pc = out["per_cell_stream"], out["per_cell"]
+    return {"value": ps["value"], "unit": "Msamples/s", "h2d_bytes_per_step": ps["h2d"], "d2h_bytes_per_step": ps["d2h"],
+            "nccl_scatter_bytes_per_step": ps["scatter"], "nccl_gather_bytes_per_step": ps["gather"],
+            "blocks_per_step": total_blocks, "seconds_per_step": ps["seconds_per_step"],
+            "api": "ShardedBlockStream.submit / collect (two steps in flight): rank-0 pinned host IQ -> H2D (copy stream) -> ONE NCCL scatter -> "
+                   "grid on every rank -> ONE NCCL gather -> D2H (copy stream) -> rank-0 host records",
+            "synchronous_call_value": pc["value"], "synchronous_call_seconds_per_step": pc["seconds_per_step"],
+            "with_on_device_best_bin_reduction": {"value": out["best_bin_stream"]["value"], "seconds_per_step": out["best_bin_stream"]["seconds_per_step"],
+                                                  "synchronous_call_value": out["best_bin"]["value"],
                                                   "d2h_bytes_per_step": out["best_bin"]["d2h"],
                                                   "nccl_gather_bytes_per_step": out["best_bin"]["gather"],
                                                   "note": "acquisition.py:179-189 per (block, PRN) row on the device: 32 B per row instead of 32 B per cell"},
-            "limiter": "the return path is serial behind the kernels: NCCL gather of every rank's per-cell records (42 KB per block) into rank 0, "
-                       "then ONE device->host copy over rank 0's PCIe link; overlapping the gather with the kernels was measured and is slower "
-                       "(profiles/ablation_r2.md: NCCL's kernels cannot co-reside with the persistent full-shared-memory correlate CTAs); "
-                       "the best-bin reduction removes 40/41 of the bytes"}
+            "limiter": "rank 0's return path: the NCCL gather of every rank's per-cell records (42 KB per block) sits between the kernel "
+                       "phases (NCCL's kernels cannot co-reside with the persistent full-shared-memory correlate CTAs: overlapping them "
+                       "was measured and is slower, profiles/ablation_r2.md), and the ONE device->host copy over rank 0's PCIe link "
+                       "(688 MB per step at 8 GPUs) only hides under the next step's kernels while it is shorter than them; "
+                       "the best-bin reduction removes 40/41 of both"}
 
 
 def secondary_rooflines(traffic, corr_ms, call_ms, blocks, n_cells, clocks):
@@ -942,7 +976,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--blocks-per-call", type=int, default=32)
-    ap.add_argument("--calls-per-step", type=int, default=64)
+    ap.add_argument("--calls-per-step", type=int, default=96)
     ap.add_argument("--ring-blocks", type=int, default=0)
     ap.add_argument("--cpu-blocks", type=int, default=4)
     ap.add_argument("--cpu-blocks-per-step", type=int, default=8)

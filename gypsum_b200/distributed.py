@@ -196,3 +196,113 @@ class ShardedBlockSearch:
         for r, s in enumerate(shares):
             full[s.start * row_bytes: s.stop * row_bytes] = raw[r * most * row_bytes: (r * most + len(s)) * row_bytes]
         return full.view(dtype).reshape((n_blocks,) + tail)
+
+
+class ShardedBlockStream:
+    """ShardedBlockSearch for a STREAM of equally shaped jobs (the receiver's steady state, and bench.py's steps): `submit`
+    enqueues one job -- rank 0's host->device copy on a copy stream, ONE scatter, the grid on every rank, ONE gather, rank 0's
+    device->host copy on a second copy stream -- and returns; `collect` waits for the oldest job in flight and hands out its
+    table.  Two jobs may be in flight: the copies of job k+1 / k-1 run on the copy engines under job k's kernels (they need
+    no SM, unlike NCCL's kernels, which is why the two collectives stay between the kernel phases on the main stream).  Every
+    rank calls submit / collect in the same order.  Equal shares only (n_blocks divisible by the world size)."""
+
+    def __init__(self, engine, device, n_blocks: int, ms_per_block: int, prn_idx, doppler_hz, kind: int, reduce: str | None = None,
+                 group=None):
+        import torch
+        import torch.distributed as dist
+
+        from gypsum_b200._native import BEST_DTYPE, RECORD_DTYPE
+
+        if reduce not in (None, "best"):
+            raise ValueError("reduce must be None or 'best'")
+        self.dist, self.engine, self.device, self.group = dist, engine, device, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if n_blocks % self.world:
+            raise ValueError("ShardedBlockStream needs n_blocks divisible by the number of ranks")
+        self.prn = np.ascontiguousarray(prn_idx, dtype=np.int32)
+        self.dop = np.ascontiguousarray(doppler_hz, dtype=np.float64)
+        self.n_blocks, self.ms, self.kind, self.reduce = n_blocks, ms_per_block, kind, reduce
+        self.share = n_blocks // self.world
+        self.per_block = ms_per_block * engine.samples_per_ms * 2  # float32 words
+        self.row_bytes = self.prn.size * (RECORD_BYTES if reduce else self.dop.size * RECORD_BYTES)
+        self.dtype = BEST_DTYPE if reduce else RECORD_DTYPE
+        self.tail = (self.prn.size,) if reduce else (self.prn.size, self.dop.size)
+        self.cuda = _is_cuda(device)
+        _adopt_current_stream(engine, device)
+        self.main = torch.cuda.current_stream(device) if self.cuda else None
+        self.s_in = torch.cuda.Stream(device) if self.cuda else None
+        self.s_out = torch.cuda.Stream(device) if self.cuda else None
+        self.slots = []
+        for _ in range(2):
+            sl = {"mine": torch.empty(self.share * self.per_block, dtype=torch.float32, device=device),
+                  "out": torch.zeros(self.share * self.row_bytes, dtype=torch.uint8, device=device)}
+            if self.rank == 0:
+                sl["all_iq"] = torch.empty(n_blocks * self.per_block, dtype=torch.float32, device=device)
+                sl["all_out"] = torch.empty(n_blocks * self.row_bytes, dtype=torch.uint8, device=device)
+                sl["h_out"] = torch.empty(n_blocks * self.row_bytes, dtype=torch.uint8, pin_memory=self.cuda)
+            if self.cuda:
+                sl["e_in"], sl["e_scattered"], sl["e_done"], sl["e_host"] = (torch.cuda.Event() for _ in range(4))
+            self.slots.append(sl)
+        self.head = self.tail_ix = 0
+        share_iq, share_out = self.share * self.per_block * 4, self.share * self.row_bytes
+        self.bytes_per_job = {"h2d": self.world * share_iq, "scatter": (self.world - 1) * share_iq,
+                              "gather": (self.world - 1) * share_out, "d2h": self.world * share_out}
+
+    @property
+    def in_flight(self) -> int:
+        return self.head - self.tail_ix
+
+    def submit(self, iq) -> None:
+        """iq: complex64[n_blocks * ms_per_block * N] on rank 0 (pinned memory = asynchronous DMA), ignored elsewhere."""
+        import torch
+
+        if self.in_flight >= 2:
+            raise RuntimeError("two jobs in flight: collect one first")
+        sl = self.slots[self.head % 2]
+        if self.rank == 0:
+            src = torch.from_numpy(np.ascontiguousarray(iq, dtype=np.complex64)[: self.n_blocks * self.per_block // 2].view(np.float32))
+            if self.cuda:
+                with torch.cuda.stream(self.s_in):
+                    self.s_in.wait_event(sl["e_scattered"])  # the scatter that last read this buffer
+                    sl["all_iq"].copy_(src, non_blocking=src.is_pinned())
+                    sl["e_in"].record(self.s_in)
+                self.main.wait_event(sl["e_in"])
+                self.main.wait_event(sl["e_host"])  # the device->host copy that last read all_out
+            else:
+                sl["all_iq"].copy_(src)
+            self.dist.scatter(sl["mine"], list(sl["all_iq"].view(self.world, -1).unbind(0)), src=0, group=self.group)
+        else:
+            self.dist.scatter(sl["mine"], None, src=0, group=self.group)
+        if self.cuda:
+            sl["e_scattered"].record(self.main)
+        self.engine.bind_iq_device(sl["mine"].data_ptr(), self.share * self.per_block // 2)
+        fn = self.engine.acquire_grid_best_device if self.reduce else self.engine.acquire_grid_device
+        fn(self.share, self.ms, self.prn, self.dop, self.kind, sl["out"].data_ptr())
+        if self.rank == 0:
+            self.dist.gather(sl["out"], list(sl["all_out"].view(self.world, -1).unbind(0)), dst=0, group=self.group)
+            if self.cuda:
+                sl["e_done"].record(self.main)
+                with torch.cuda.stream(self.s_out):
+                    self.s_out.wait_event(sl["e_done"])
+                    sl["h_out"].copy_(sl["all_out"], non_blocking=True)
+                    sl["e_host"].record(self.s_out)
+            else:
+                sl["h_out"].copy_(sl["all_out"])
+        else:
+            self.dist.gather(sl["out"], None, dst=0, group=self.group)
+            if self.cuda:
+                sl["e_done"].record(self.main)
+        self.head += 1
+
+    def collect(self):
+        """Rank 0: the oldest job's table as a view of its pinned receive buffer (valid until two more jobs were submitted);
+        other ranks: None (after their share of that job has left the device)."""
+        if not self.in_flight:
+            raise RuntimeError("no job in flight")
+        sl = self.slots[self.tail_ix % 2]
+        self.tail_ix += 1
+        if self.cuda:
+            (sl["e_host"] if self.rank == 0 else sl["e_done"]).synchronize()
+        if self.rank != 0:
+            return None
+        return sl["h_out"].numpy().view(self.dtype).reshape((self.n_blocks,) + self.tail)

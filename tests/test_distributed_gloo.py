@@ -93,6 +93,18 @@ def _block_worker(rank, world, port, q):
     moved_best = search.last_bytes
     view = search.acquire_blocks(x, 5, 1, np.array([8, 0]), [-500.0, 0.0], 2, copy=False)
     assert view is None or np.array_equal(view["peak"], full["peak"])
+    # the pipelined stream form (equal shares): 6 blocks, two jobs in flight, tables identical to the one-call form
+    from gypsum_b200.distributed import ShardedBlockStream
+    x6 = o.synth_iq(7, 2046, 6, 2046000, [(9, -500.0, 1234, 0.0, 0.4)]) if rank == 0 else None
+    if world in (2, 3):
+        stream = ShardedBlockStream(_OracleEngine(), "cpu", 6, 1, np.array([8, 0]), [-500.0, 0.0], 2)
+        stream.submit(x6)
+        stream.submit(x6)
+        a = stream.collect()
+        b = stream.collect()
+        one = search.acquire_blocks(x6, 6, 1, np.array([8, 0]), [-500.0, 0.0], 2)
+        assert a is None or (np.array_equal(a["peak"], one["peak"]) and np.array_equal(b["argmax"], one["argmax"]))
+        assert stream.bytes_per_job["gather"] == (world - 1) * (6 // world) * 2 * 2 * 32
     q.put((rank, None if full is None else (full["peak"].copy(), full["argmax"].copy(), best.copy(), moved, dict(moved_best))))
     dist.destroy_process_group()
 
