@@ -6,7 +6,7 @@ per other BASELINE configuration.
     python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm (numpy) on the host cores
 
 One STEP = one pass of the hot path over one batch of synthetic input: `calls_per_step` x `blocks_per_call` independent
-1-ms IQ blocks @ 2.046 Msps (default 96 x 32 = 3072 blocks, 6.3 Msamples, ~27 ms of GPU work), each searched over the full
+1-ms IQ blocks @ 2.046 Msps (default 24 x 128 = 3072 blocks, 6.3 Msamples, ~26 ms of GPU work), each searched over the full
 32 PRN x 41 Doppler (+-10 kHz / 500 Hz) grid with 1 ms of non-coherent integration -- i.e. 3072 x (BASELINE config 2).
 The metric is per input sample, so the batch only sets how much work one step carries.
 
@@ -535,7 +535,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
                 "parallelism": (f"value: blocks sharded over {world} GPU(s), no collective; "
                                 + ("e2e: one process" if world == 1 else "e2e: rank-0 host -> NCCL scatter -> grid per rank -> NCCL gather -> rank-0 host")),
                 "l2": f"inputs larger than L2: IQ ring of {ring_blocks} distinct blocks = {ring_blocks * block_bytes >> 20} MiB per GPU, "
-                      "fresh blocks every call; the spectra scratch (43 MB per call) is written and re-read by the two kernels of a call",
+                      f"fresh blocks every call; the spectra scratch ({B * 1.34:.0f} MB per call) is written and re-read by the two kernels of a call",
             },
             "e2e": e2e,
             "single_block": single_block,
@@ -766,17 +766,21 @@ def bench_config5(g, cpu, peak_gbs, sampler, args) -> dict:
         ms = g.timed(job, 2, first=1) / 2
         t1 = time.perf_counter()
 
+        per_launch = 24  # what the 512 MB spectra scratch holds at this rate (21 MB per block)
+
         def part(k):  # per-kernel timing on a slice (event-bracketed launches)
-            eng.bind_iq_device(dev.data_ptr() + (k % 10) * 30 * n * 8, 30 * n)
-            eng.acquire_grid_device(30, 1, prn, dop, _native.NON_COHERENT, rec_dev.data_ptr())
+            eng.bind_iq_device(dev.data_ptr() + (k % 10) * 2 * per_launch * n * 8, 2 * per_launch * n)
+            eng.acquire_grid_device(2 * per_launch, 1, prn, dop, _native.NON_COHERENT, rec_dev.data_ptr())
 
         spec_ms, spec_n, corr_ms, corr_n = kernel_times(eng, part, 3)
-        blocks_per_launch = 30 * 3 / max(corr_n, 1)
-        # host to host: pipelined batches
-        bb = 25
+        blocks_per_launch = 2 * per_launch * 3 / max(corr_n, 1)
+        # host to host: pipelined batches (41 x 24 blocks + one of 16)
+        bb, rem = per_launch, nb % per_launch
         gs = _native.GridStream(eng, bb, 1, prn, dop, _native.NON_COHERENT, depth=3)
+        gs_rem = _native.GridStream(eng, rem, 1, prn, dop, _native.NON_COHERENT, depth=1) if rem else None
         outs = [torch.empty(bb * n_cells * 32, dtype=torch.uint8).pin_memory() for _ in range(3)]
         outs_np = [o_.numpy().view(_native.RECORD_DTYPE).reshape(bb, N_PRN, len(dop)) for o_ in outs]
+        out_rem = np.empty((max(rem, 1), N_PRN, len(dop)), dtype=_native.RECORD_DTYPE)
 
         def e2e_job(k):
             for j in range(nb // bb):
@@ -785,10 +789,15 @@ def bench_config5(g, cpu, peak_gbs, sampler, args) -> dict:
                 gs.submit(host.data_ptr() + j * bb * n * 8, outs_np[j % 3])
             while gs.in_flight:
                 gs.collect()
+            if gs_rem is not None:
+                gs_rem.submit(host.data_ptr() + (nb - rem) * n * 8, out_rem)
+                gs_rem.collect()
 
         e2e_job(0)
         sec = g.wall(e2e_job, 2, first=1) / 2
         gs.close()
+        if gs_rem is not None:
+            gs_rem.close()
         x2 = host.numpy()[:2]
         ref, cpu_sec = cpu.grid(x2, fs, n, DOPPLERS_81)
         eng.upload_iq(x2.reshape(-1))
@@ -805,7 +814,7 @@ def bench_config5(g, cpu, peak_gbs, sampler, args) -> dict:
                          "other_kernels_ms_per_launch": {"k_doppler_spectra": spec_ms}, "traffic": traffic_for("config5_correlate_dram_bytes_per_launch")},
             "cpu_baseline": {"value": 2 * n / cpu_sec / 1e6, "unit": "Msamples/s", "cores": cpu.cores, "kind": "port",
                              "sample": "2 of the 1000 blocks, full 32x81 grid, cells over all cores (the job's CPU time is this x 500, extrapolated)"},
-            "parity_checked_cells": cells, "l2": "job input 125 MiB (~L2) + 20 MB of spectra scratch per 3-block launch",
+            "parity_checked_cells": cells, "l2": "job input 125 MiB (~L2); 509 MB of spectra scratch written and re-read per 24-block launch pair (far beyond L2)",
             "clocks": sampler.window(t0, t1) if sampler else None})
     else:
         from gypsum_b200.distributed import ShardedBlockSearch
@@ -975,8 +984,8 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--blocks-per-call", type=int, default=32)
-    ap.add_argument("--calls-per-step", type=int, default=96)
+    ap.add_argument("--blocks-per-call", type=int, default=128)
+    ap.add_argument("--calls-per-step", type=int, default=24)
     ap.add_argument("--ring-blocks", type=int, default=0)
     ap.add_argument("--cpu-blocks", type=int, default=4)
     ap.add_argument("--cpu-blocks-per-step", type=int, default=8)
