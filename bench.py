@@ -6,7 +6,7 @@ per other BASELINE configuration.
     python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm (numpy) on the host cores
 
 One STEP = one pass of the hot path over one batch of synthetic input: `calls_per_step` x `blocks_per_call` independent
-1-ms IQ blocks @ 2.046 Msps (default 24 x 128 = 3072 blocks, 6.3 Msamples, ~26 ms of GPU work), each searched over the full
+1-ms IQ blocks @ 2.046 Msps (default 12 x 256 = 3072 blocks, 6.3 Msamples, ~25 ms of GPU work), each searched over the full
 32 PRN x 41 Doppler (+-10 kHz / 500 Hz) grid with 1 ms of non-coherent integration -- i.e. 3072 x (BASELINE config 2).
 The metric is per input sample, so the batch only sets how much work one step carries.
 
@@ -984,8 +984,8 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--blocks-per-call", type=int, default=128)
-    ap.add_argument("--calls-per-step", type=int, default=24)
+    ap.add_argument("--blocks-per-call", type=int, default=256)
+    ap.add_argument("--calls-per-step", type=int, default=12)
     ap.add_argument("--ring-blocks", type=int, default=0)
     ap.add_argument("--cpu-blocks", type=int, default=4)
     ap.add_argument("--cpu-blocks-per-step", type=int, default=8)

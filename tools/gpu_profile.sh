@@ -6,8 +6,8 @@ TAG=${1:-r2}
 mkdir -p gpurun_out
 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err
 tail -c 1500 gpurun_out/bench_${TAG}.json
-SMALL="--steps 2 --warmup 1 --calls-per-step 4 --cpu-blocks 1 --no-configs"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 10 -c 120 --csv \
+SMALL="--steps 2 --warmup 1 --calls-per-step 2 --cpu-blocks 1 --no-configs"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 6 -c 60 --csv \
     --log-file gpurun_out/launches_${TAG}.csv python bench.py $SMALL > gpurun_out/ncu_bench_${TAG}.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_correlate_w2048 -s 10 -c 2 \
     -f -o gpurun_out/prof_corr_${TAG} python bench.py $SMALL > gpurun_out/ncu_full_${TAG}.log 2>&1
