@@ -118,6 +118,7 @@ struct gb200_engine {
         std::vector<double> dop;
         std::vector<int> prn;
         const void *iq_dev = nullptr, *rec_dev = nullptr, *iq_stage = nullptr, *rec_stage = nullptr, *spec = nullptr;
+        const void *d_dop = nullptr, *d_prn = nullptr, *crep = nullptr;  // what the captured kernels dereference besides the above
         cudaStream_t stream = nullptr;
     } hg;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[2];
@@ -300,6 +301,29 @@ int check_common(gb200_engine* e, int n_ms, int kind) {
     return GB200_OK;
 }
 
+// The grid's axes (PRN rows in d_ints, Doppler bins in d_doppler) are uploaded only when they changed -- or when a list-mode
+// call (gb200_acquire_cells / gb200_detect) has reused those device buffers since.
+int upload_grid_axes(gb200_engine* e, const int32_t* prn_idx, int P, const double* dop, int D) {
+    const bool same = e->grid_cache_valid && static_cast<int>(e->doppler_cache.size()) == D &&
+                      static_cast<int>(e->prn_cache.size()) == P &&
+                      memcmp(e->doppler_cache.data(), dop, sizeof(double) * D) == 0 &&
+                      memcmp(e->prn_cache.data(), prn_idx, sizeof(int) * P) == 0;
+    if (same) return GB200_OK;
+    GB_CUDA(e, cudaStreamSynchronize(e->stream));  // staging buffers may still be in flight
+    GB_CUDA(e, e->d_doppler.ensure(D));
+    GB_CUDA(e, e->d_ints.ensure(P));
+    GB_CUDA(e, e->h_doubles.ensure(D));
+    GB_CUDA(e, e->h_ints.ensure(P));
+    memcpy(e->h_doubles.p, dop, sizeof(double) * D);
+    memcpy(e->h_ints.p, prn_idx, sizeof(int) * P);
+    GB_CUDA(e, cudaMemcpyAsync(e->d_doppler.p, e->h_doubles.p, sizeof(double) * D, cudaMemcpyHostToDevice, e->stream));
+    GB_CUDA(e, cudaMemcpyAsync(e->d_ints.p, e->h_ints.p, sizeof(int) * P, cudaMemcpyHostToDevice, e->stream));
+    e->doppler_cache.assign(dop, dop + D);
+    e->prn_cache.assign(prn_idx, prn_idx + P);
+    e->grid_cache_valid = true;
+    return GB200_OK;
+}
+
 // grid mode: all cells of n_blocks x prn list x doppler list; records written to rec_dev (device)
 int run_grid(gb200_engine* e, int n_blocks, int M, const int32_t* prn_idx, int P, const double* dop, int D, int kind,
              CellRecord* rec_dev) {
@@ -312,25 +336,8 @@ int run_grid(gb200_engine* e, int n_blocks, int M, const int32_t* prn_idx, int P
     for (int i = 0; i < P; ++i)
         if (prn_idx[i] < 0 || prn_idx[i] >= e->n_prn) GB_FAIL(e, GB200_EINVAL, "prn index %d out of range", prn_idx[i]);
 
-    // (re)upload the axes only when they changed
-    const bool same = e->grid_cache_valid && static_cast<int>(e->doppler_cache.size()) == D &&
-                      static_cast<int>(e->prn_cache.size()) == P &&
-                      memcmp(e->doppler_cache.data(), dop, sizeof(double) * D) == 0 &&
-                      memcmp(e->prn_cache.data(), prn_idx, sizeof(int) * P) == 0;
-    if (!same) {
-        GB_CUDA(e, cudaStreamSynchronize(e->stream));  // staging buffers may still be in flight
-        GB_CUDA(e, e->d_doppler.ensure(D));
-        GB_CUDA(e, e->d_ints.ensure(P));
-        GB_CUDA(e, e->h_doubles.ensure(D));
-        GB_CUDA(e, e->h_ints.ensure(P));
-        memcpy(e->h_doubles.p, dop, sizeof(double) * D);
-        memcpy(e->h_ints.p, prn_idx, sizeof(int) * P);
-        GB_CUDA(e, cudaMemcpyAsync(e->d_doppler.p, e->h_doubles.p, sizeof(double) * D, cudaMemcpyHostToDevice, e->stream));
-        GB_CUDA(e, cudaMemcpyAsync(e->d_ints.p, e->h_ints.p, sizeof(int) * P, cudaMemcpyHostToDevice, e->stream));
-        e->doppler_cache.assign(dop, dop + D);
-        e->prn_cache.assign(prn_idx, prn_idx + P);
-        e->grid_cache_valid = true;
-    }
+    rc = upload_grid_axes(e, prn_idx, P, dop, D);
+    if (rc) return rc;
 
     const size_t unit = unit_floats2(e, M);
     const size_t per_block = unit * D;
@@ -807,10 +814,21 @@ int gb200_acquire_grid_host(gb200_engine* e, const float* iq_host, int n_blocks,
     e->iq = e->iq_own.p;
     e->iq_samples = static_cast<int64_t>(n_iq);
 
+    // The captured kernels read the axes from d_doppler / d_ints and the replica spectra from crep: make sure those hold THIS
+    // grid's axes now (a list-mode call may have reused them since the last replay; cheap when nothing changed), and treat a
+    // moved buffer (gb200_set_replicas with a larger table, a larger list-mode call) as a new shape.
+    {
+        if (e->n_prn == 0) GB_FAIL(e, GB200_ESTATE, "no PRN replicas loaded (gb200_set_replicas)");
+        for (int i = 0; i < P; ++i)
+            if (prn_idx[i] < 0 || prn_idx[i] >= e->n_prn) GB_FAIL(e, GB200_EINVAL, "prn index %d out of range", prn_idx[i]);
+        int rc = upload_grid_axes(e, prn_idx, P, dop, D);
+        if (rc) return rc;
+    }
     auto& g = e->hg;
     const bool same = g.seen && g.n_blocks == n_blocks && g.M == M && g.P == P && g.D == D && g.kind == kind &&
                       g.iq_dev == e->iq_own.p && g.rec_dev == e->d_records.p && g.iq_stage == e->h_iq.p &&
                       g.rec_stage == e->h_records.p && g.spec == e->spec.p && g.stream == e->stream &&
+                      g.d_dop == e->d_doppler.p && g.d_prn == e->d_ints.p && g.crep == e->crep.p &&
                       memcmp(g.dop.data(), dop, sizeof(double) * D) == 0 && memcmp(g.prn.data(), prn_idx, sizeof(int) * P) == 0;
     // Small grids: the correlate kernel stores its 32-byte records straight into the pinned (device-mapped under UVA) staging
     // buffer -- posted PCIe writes at the kernel's tail instead of a separate copy node behind it.
@@ -863,6 +881,9 @@ int gb200_acquire_grid_host(gb200_engine* e, const float* iq_host, int n_blocks,
             g.iq_stage = e->h_iq.p;
             g.rec_stage = e->h_records.p;
             g.spec = e->spec.p;
+            g.d_dop = e->d_doppler.p;
+            g.d_prn = e->d_ints.p;
+            g.crep = e->crep.p;
             g.stream = e->stream;
             g.seen = 1;
         }

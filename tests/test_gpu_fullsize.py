@@ -88,6 +88,18 @@ def test_config2_all_1312_cells(engine_for):
     for other in (rec_h, rec_g, rec_r):
         for k in ("peak", "argmax", "sum", "count"):
             assert np.array_equal(other[k], rec[k]), k
+    # the replayed graph reads the grid's axes and the replica spectra from device buffers other calls reuse: a list-mode call
+    # with other Dopplers, a different grid, and a re-loaded replica table in between must not leak into the next replay
+    eng.acquire_cells([3, 4], [123.0, -456.0], 1)
+    eng.acquire_grid(1, 1, [5], [777.0])
+    again = eng.acquire_grid_host(x, 1, 1, np.arange(32), dop)[0]
+    assert all(np.array_equal(again[k], rec[k]) for k in ("peak", "argmax", "sum", "count"))
+    chips = np.stack([o.ca_code(sv) for sv in range(1, 33)]).astype(np.uint8)
+    eng.set_replicas(chips[::-1].copy())  # row a now holds SV 32 - a
+    flipped = eng.acquire_grid_host(x, 1, 1, np.arange(32), dop)[0]
+    assert all(np.array_equal(flipped[k], rec[k][::-1]) for k in ("peak", "argmax", "sum", "count"))
+    eng.set_replicas(chips)
+    eng.upload_iq(x)
     best = eng.acquire_grid_best(1, 1, np.arange(32), dop)[0]
     for a in range(32):  # acquisition.py:179-189 per PRN row
         b = int(np.argmax(rec["peak"][a]))
