@@ -51,5 +51,35 @@ for n, m in ((2046, 2), (4092, 1)):
             outs.append(gs.collect().copy())
         assert all(int(u["argmax"][0, 0, 7]) == 777 for u in outs)
         gs.close()
+        # round 2: multi-ms one-warp kernel, graph-replayed host grid, best-bin reduction, device ring, channel pool with
+        # subset launches + undo, generic-replica kernel
+        x10 = o.synth_iq(4, n, 3, fs, [(25, 1500.0, 777, 0.3, 0.3)])
+        eng.upload_iq(x10)
+        g3 = eng.acquire_grid(1, 3, np.arange(32), dop)
+        assert int(g3["argmax"][0, 24, 7]) == 777
+        for _ in range(3):
+            gh = eng.acquire_grid_host(x10, 1, 3, np.arange(32), dop)
+        assert np.array_equal(gh["argmax"], g3["argmax"])
+        eng.upload_iq(x10)
+        best = eng.acquire_grid_best(1, 3, np.arange(32), dop)
+        assert int(best["code_phase"][0, 24]) == 777 and float(best["doppler"][0, 24]) == 1500.0
+        ring = _native.Ring(eng, 4)
+        for k in range(6):
+            ring.append(xs[k * n:(k + 1) * n])
+        ring.bind_newest(3)
+        pool = _native.Tracker.pool(eng, 4)
+        pool.reset_channel(2, 24, 1500.0, 0.0, 777)
+        pool.reset_channel(0, 6, -100.0, 0.0, 5)
+        r1 = pool.process_channels([2, 0], 1, [0.003], keep_undo=True)
+        pool.undo_channel(0)
+        r2 = pool.process_channels([0], 1, [0.003])
+        assert r1["symbol"][1, 0] == r2["symbol"][0, 0]
+        pool.close()
+        ring.close()
+        eng.upload_iq(x10)
+        rng = np.random.default_rng(0)
+        odd = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+        pr = eng.correlation_profile_replica(odd, 250.0, 2, _native.NON_COHERENT)
+        assert pr.shape == (n,)
     eng.close()
 print("sanitize_small ok")
