@@ -75,8 +75,6 @@ if os.path.exists(bp) and os.path.getsize(bp):
 open(os.path.join(out_dir, f"ncu_{tag}.md"), "w").write("\n".join(lines) + "\n")
 json.dump(summary, open(os.path.join(out_dir, f"summary_{tag}.json"), "w"), indent=1)
 k = summary["kernels"].get("void gb::k_correlate_cells<8, 2, 0>") or next((v for n, v in summary["kernels"].items() if "correlate" in n), None)
-if k:
-    json.dump({"tag": tag, "correlate_cells_dram_bytes_per_launch": k["dram_bytes_per_launch"],
-               "note": "dram__bytes_read.sum + dram__bytes_write.sum of one k_correlate_cells launch (32 blocks x 1312 cells), ncu --set full"},
-              open(os.path.join(out_dir, "traffic.json"), "w"), indent=1)
+if k:  # printed for the hand-maintained profiles/traffic.json (which also keeps the other launch sizes and says how it was taken)
+    print("correlate dram bytes per launch:", k["dram_bytes_per_launch"])
 print("\n".join(lines[:60]))
