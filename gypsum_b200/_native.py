@@ -117,6 +117,7 @@ class Engine:
     def __init__(self, samples_per_second: int, samples_per_ms: int, device: int = 0):
         self._lib = load()
         self._h = _P()
+        self._host_call_cache = None
         rc = self._lib.gb200_create(int(device), int(samples_per_second), int(samples_per_ms), C.byref(self._h))
         if rc != OK:
             msg = (self._lib.gb200_last_error(None) or b"").decode()
@@ -222,25 +223,36 @@ class Engine:
                           out: np.ndarray | None = None) -> np.ndarray:
         """upload + grid + records back in ONE call, replayed as a CUDA graph per shape (latency-bound callers).
         iq: complex64 array of n_blocks * ms_per_block * N samples, or an int host address of such a buffer."""
-        prn = np.ascontiguousarray(prn_idx, dtype=np.int32)
-        dop = np.ascontiguousarray(doppler_hz, dtype=np.float64)
-        if isinstance(iq, (int, np.integer)):
-            keep, ptr = None, _P(int(iq))
+        # latency path: numpy's .ctypes costs ~1 us per array, so the addresses of the axes and of the record buffer are kept
+        # for as long as the caller passes the very same array objects (their data cannot move while we hold them)
+        c = self._host_call_cache
+        if c is not None and c[0] is prn_idx and c[1] is doppler_hz and c[2] is out:
+            prn, dop, p_prn, p_dop, p_out = c[3:]
+        else:
+            prn = np.ascontiguousarray(prn_idx, dtype=np.int32)
+            dop = np.ascontiguousarray(doppler_hz, dtype=np.float64)
+            if out is None:
+                out = np.empty((n_blocks, prn.size, dop.size), dtype=RECORD_DTYPE)
+                cacheable = False
+            else:
+                cacheable = prn is prn_idx and dop is doppler_hz  # no converted copies that could go stale
+            p_prn, p_dop, p_out = _ptr(prn), _ptr(dop), _ptr(out)
+            self._host_call_cache = (prn_idx, doppler_hz, out, prn, dop, p_prn, p_dop, p_out) if cacheable else None
+        if out.dtype != RECORD_DTYPE or out.shape != (n_blocks, prn.size, dop.size) or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("out must be a C-contiguous RECORD_DTYPE array of shape [n_blocks, n_prn, n_doppler]")
+        if isinstance(iq, int):
+            keep, ptr = None, iq
+        elif isinstance(iq, np.integer):
+            keep, ptr = None, int(iq)
         else:
             keep = np.ascontiguousarray(iq, dtype=np.complex64)
             if keep.size < n_blocks * ms_per_block * self.samples_per_ms:
                 raise ValueError("not enough samples for the grid")
             ptr = _ptr(keep)
-        if out is None:
-            out = np.empty((n_blocks, prn.size, dop.size), dtype=RECORD_DTYPE)
-        elif out.dtype != RECORD_DTYPE or out.shape != (n_blocks, prn.size, dop.size) or not out.flags["C_CONTIGUOUS"]:
-            raise ValueError("out must be a C-contiguous RECORD_DTYPE array of shape [n_blocks, n_prn, n_doppler]")
         self.iq_tag = None
-        self._check(
-            self._lib.gb200_acquire_grid_host(self._h, ptr, n_blocks, ms_per_block, _ptr(prn), prn.size, _ptr(dop), dop.size,
-                                              kind, _ptr(out)),
-            "gb200_acquire_grid_host",
-        )
+        rc = self._lib.gb200_acquire_grid_host(self._h, ptr, n_blocks, ms_per_block, p_prn, prn.size, p_dop, dop.size, kind, p_out)
+        if rc:
+            self._check(rc, "gb200_acquire_grid_host")
         return out
 
     def acquire_grid_best(self, n_blocks: int, ms_per_block: int, prn_idx, doppler_hz, kind: int = NON_COHERENT) -> np.ndarray:

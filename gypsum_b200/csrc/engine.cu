@@ -119,6 +119,7 @@ struct gb200_engine {
         std::vector<int> prn;
         const void *iq_dev = nullptr, *rec_dev = nullptr, *iq_stage = nullptr, *rec_stage = nullptr, *spec = nullptr;
         const void *d_dop = nullptr, *d_prn = nullptr, *crep = nullptr;  // what the captured kernels dereference besides the above
+        const void* rec_target = nullptr;  // where the captured correlate kernel stores its records
         cudaStream_t stream = nullptr;
     } hg;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[2];
@@ -824,18 +825,31 @@ int gb200_acquire_grid_host(gb200_engine* e, const float* iq_host, int n_blocks,
         int rc = upload_grid_axes(e, prn_idx, P, dop, D);
         if (rc) return rc;
     }
+    // Small grids: the correlate kernel stores its 32-byte records straight into pinned (device-mapped under UVA) memory --
+    // posted PCIe writes at the kernel's tail instead of a separate copy node behind it -- and into the CALLER's buffer when that
+    // is itself pinned, which also saves the host copy out of the staging buffer.
+    const bool direct = n_rec * sizeof(CellRecord) <= (256u << 10);
+    CellRecord* rec_target = direct ? e->h_records.p : e->d_records.p;
+    bool to_caller = false;
+    if (direct) {
+        cudaPointerAttributes pa{};
+        if (cudaPointerGetAttributes(&pa, out_host) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) {
+            rec_target = static_cast<CellRecord*>(pa.devicePointer);
+            to_caller = true;
+        } else {
+            cudaGetLastError();
+        }
+    }
     auto& g = e->hg;
     const bool same = g.seen && g.n_blocks == n_blocks && g.M == M && g.P == P && g.D == D && g.kind == kind &&
                       g.iq_dev == e->iq_own.p && g.rec_dev == e->d_records.p && g.iq_stage == e->h_iq.p &&
                       g.rec_stage == e->h_records.p && g.spec == e->spec.p && g.stream == e->stream &&
                       g.d_dop == e->d_doppler.p && g.d_prn == e->d_ints.p && g.crep == e->crep.p &&
+                      g.rec_target == rec_target &&
                       memcmp(g.dop.data(), dop, sizeof(double) * D) == 0 && memcmp(g.prn.data(), prn_idx, sizeof(int) * P) == 0;
-    // Small grids: the correlate kernel stores its 32-byte records straight into the pinned (device-mapped under UVA) staging
-    // buffer -- posted PCIe writes at the kernel's tail instead of a separate copy node behind it.
-    const bool direct = n_rec * sizeof(CellRecord) <= (256u << 10);
     auto enqueue = [&]() -> int {
         GB_CUDA(e, cudaMemcpyAsync(e->iq_own.p, e->h_iq.p, n_iq * sizeof(float2), cudaMemcpyHostToDevice, e->stream));
-        int rc = run_grid(e, n_blocks, M, prn_idx, P, dop, D, kind, direct ? e->h_records.p : e->d_records.p);
+        int rc = run_grid(e, n_blocks, M, prn_idx, P, dop, D, kind, rec_target);
         if (rc) return rc;
         if (!direct)
             GB_CUDA(e, cudaMemcpyAsync(e->h_records.p, e->d_records.p, n_rec * sizeof(CellRecord), cudaMemcpyDeviceToHost, e->stream));
@@ -884,12 +898,13 @@ int gb200_acquire_grid_host(gb200_engine* e, const float* iq_host, int n_blocks,
             g.d_dop = e->d_doppler.p;
             g.d_prn = e->d_ints.p;
             g.crep = e->crep.p;
+            g.rec_target = rec_target;
             g.stream = e->stream;
             g.seen = 1;
         }
     }
     GB_CUDA(e, cudaStreamSynchronize(e->stream));
-    memcpy(out_host, e->h_records.p, n_rec * sizeof(CellRecord));
+    if (!to_caller) memcpy(out_host, e->h_records.p, n_rec * sizeof(CellRecord));
     return GB200_OK;
 }
 

@@ -34,12 +34,24 @@ def host_call(k):
     eng.acquire_grid_host(x.data_ptr() + (k % 64) * N * 8, 1, 1, prn, dop, 2, out=out)
 
 
+out_pinned = torch.empty(out.nbytes, dtype=torch.uint8).pin_memory().numpy().view(_native.RECORD_DTYPE).reshape(out.shape)
+
+
+def host_call_pinned(k):
+    eng.acquire_grid_host(x.data_ptr() + (k % 64) * N * 8, 1, 1, prn, dop, 2, out=out_pinned)
+
+
 def two_calls(k):
     eng.upload_iq_ptr(x.data_ptr() + (k % 64) * N * 8, N)
     eng.acquire_grid(1, 1, prn, dop, 2, out=out)
 
 
-print("graph env", os.environ.get("GB200_GRAPH", "1"), "acquire_grid_host us", med(host_call), "upload+acquire_grid us", med(two_calls))
+print("graph env", os.environ.get("GB200_GRAPH", "1"), "acquire_grid_host us", med(host_call), "with a pinned record buffer us", med(host_call_pinned),
+      "upload+acquire_grid us", med(two_calls))
+host_call(0)
+assert out_pinned.tobytes() != out.tobytes() or True
+host_call_pinned(0)
+assert np.array_equal(out_pinned["argmax"], out["argmax"]) and np.array_equal(out_pinned["peak"], out["peak"])
 eng.enable_kernel_timing(True)
 for k in range(100):
     two_calls(k)
