@@ -811,7 +811,21 @@ int gb200_acquire_grid_host(gb200_engine* e, const float* iq_host, int n_blocks,
     GB_CUDA(e, e->h_iq.ensure(n_iq));
     GB_CUDA(e, e->d_records.ensure(n_rec));
     GB_CUDA(e, e->h_records.ensure(n_rec));
-    memcpy(e->h_iq.p, iq_host, n_iq * sizeof(float2));
+    // Large pinned inputs (a 10-ms window is 327 KB) are copied by the DMA engine straight from the caller's buffer: staging them
+    // would cost a 15-20 us host memcpy.  The copy node of the graph has its source baked in, so those calls launch eagerly
+    // (1.7 us more than a replay on this host, profiles/launch_latency_r2.log).  Small inputs are staged and replayed.
+    const float2* h2d_src = e->h_iq.p;
+    bool eager_src = false;
+    if (n_iq * sizeof(float2) > (64u << 10)) {
+        cudaPointerAttributes pa{};
+        if (cudaPointerGetAttributes(&pa, iq_host) == cudaSuccess && pa.type == cudaMemoryTypeHost) {
+            h2d_src = reinterpret_cast<const float2*>(iq_host);
+            eager_src = true;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    if (!eager_src) memcpy(e->h_iq.p, iq_host, n_iq * sizeof(float2));
     e->iq = e->iq_own.p;
     e->iq_samples = static_cast<int64_t>(n_iq);
 
@@ -848,14 +862,17 @@ int gb200_acquire_grid_host(gb200_engine* e, const float* iq_host, int n_blocks,
                       g.rec_target == rec_target &&
                       memcmp(g.dop.data(), dop, sizeof(double) * D) == 0 && memcmp(g.prn.data(), prn_idx, sizeof(int) * P) == 0;
     auto enqueue = [&]() -> int {
-        GB_CUDA(e, cudaMemcpyAsync(e->iq_own.p, e->h_iq.p, n_iq * sizeof(float2), cudaMemcpyHostToDevice, e->stream));
+        GB_CUDA(e, cudaMemcpyAsync(e->iq_own.p, h2d_src, n_iq * sizeof(float2), cudaMemcpyHostToDevice, e->stream));
         int rc = run_grid(e, n_blocks, M, prn_idx, P, dop, D, kind, rec_target);
         if (rc) return rc;
         if (!direct)
             GB_CUDA(e, cudaMemcpyAsync(e->h_records.p, e->d_records.p, n_rec * sizeof(CellRecord), cudaMemcpyDeviceToHost, e->stream));
         return GB200_OK;
     };
-    if (same && g.exec) {
+    if (eager_src) {
+        int rc = enqueue();
+        if (rc) return rc;
+    } else if (same && g.exec) {
         GB_CUDA(e, cudaGraphLaunch(g.exec, e->stream));
         e->launches += 2;
     } else if (same && !g.exec && g.seen == 1) {
