@@ -393,6 +393,27 @@ int run_grid(gb200_engine* e, int n_blocks, int M, const int32_t* prn_idx, int P
         ca.prn_idx = e->d_ints.p;
         ca.cell_probe = nullptr;
         const int grid = std::min(ca.n_groups, e->num_sms);
+        // L2 windows of the one-warp kernel (see the kernel): a batch whose spectra exceed L2 is walked in equal runs of units of
+        // about GB200_L2_WINDOW_MB (default 40; 0 = off) -- but only when a window still gives every CTA at least 8 groups, so that
+        // the uneven part of the split stays small (config 5's heavy cells would need a 114 MB window: not windowed).
+        static const size_t win_bytes = static_cast<size_t>(std::max(0, env_int("GB200_L2_WINDOW_MB", 40))) << 20;
+        ca.win_chunks = 0;
+        const size_t batch_bytes = static_cast<size_t>(nbb) * per_block * sizeof(float2);
+        if (nw && win_bytes && batch_bytes > win_bytes + win_bytes / 2) {
+            const long long n_win = static_cast<long long>((batch_bytes + win_bytes - 1) / win_bytes);
+            long long wc = (chunks + n_win - 1) / n_win;
+            // a window whose P * wc groups divide evenly among the CTAs, when one exists within a quarter of the target size
+            long long q = grid, gcd_a = P, gcd_b = grid;
+            while (gcd_b) {
+                const long long t = gcd_a % gcd_b;
+                gcd_a = gcd_b;
+                gcd_b = t;
+            }
+            q = grid / gcd_a;
+            const long long even = ((wc + q / 2) / q) * q;
+            if (even > 0 && even * 4 >= wc * 3 && even * 4 <= wc * 5) wc = even;
+            if (wc * P >= 8LL * grid && wc < chunks) ca.win_chunks = static_cast<int>(wc);
+        }
         {
             TimedLaunch tl(e, 1);
             if (nw) GB_CUDA(e, launch_correlate_w2048(ca, nw, grid, e->stream));

@@ -33,6 +33,7 @@ struct CorrelateArgs {
     int n_groups;
     // grid mode (cells = blocks x prn list x doppler list)
     int grid_mode, P, D, n_blocks, chunks;  // chunks = ceil(n_blocks * D / cells_per_group): groups per PRN
+    int win_chunks;  // k_correlate_w2048, grid mode: chunks per L2 window (0 = the whole batch is one window), see the kernel
     const int* prn_idx;           // [P]
     // list mode (cells sorted by PRN)
     const int* grp_first;
