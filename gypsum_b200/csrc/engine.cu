@@ -394,8 +394,8 @@ int run_grid(gb200_engine* e, int n_blocks, int M, const int32_t* prn_idx, int P
         ca.cell_probe = nullptr;
         const int grid = std::min(ca.n_groups, e->num_sms);
         // L2 windows of the one-warp kernel (see the kernel): a batch whose spectra exceed L2 is walked in equal runs of units of
-        // about GB200_L2_WINDOW_MB (default 40; 0 = off) -- but only when a window still gives every CTA at least 8 groups, so that
-        // the uneven part of the split stays small (config 5's heavy cells would need a 114 MB window: not windowed).
+        // about GB200_L2_WINDOW_MB (default 40; 0 = off), as long as a window still gives every CTA at least two groups (config 5's
+        // heavy cells: 2.8 groups per CTA and window; the kernel's round-robin of the extra groups keeps the CTAs together).
         static const size_t win_bytes = static_cast<size_t>(std::max(0, env_int("GB200_L2_WINDOW_MB", 40))) << 20;
         ca.win_chunks = 0;
         const size_t batch_bytes = static_cast<size_t>(nbb) * per_block * sizeof(float2);
@@ -412,7 +412,8 @@ int run_grid(gb200_engine* e, int n_blocks, int M, const int32_t* prn_idx, int P
             q = grid / gcd_a;
             const long long even = ((wc + q / 2) / q) * q;
             if (even > 0 && even * 4 >= wc * 3 && even * 4 <= wc * 5) wc = even;
-            if (wc * P >= 8LL * grid && wc < chunks) ca.win_chunks = static_cast<int>(wc);
+            static const int min_groups = env_int("GB200_L2_WINDOW_MIN_GROUPS", 2);
+            if (wc * P >= static_cast<long long>(min_groups) * grid && wc < chunks) ca.win_chunks = static_cast<int>(wc);
         }
         {
             TimedLaunch tl(e, 1);
