@@ -203,3 +203,45 @@ def oracle_channel_entry(args):
         r = tr.step(x[k * n:(k + 1) * n], a, b)
         rows.append((r["symbol"], r["code_phase"], tr.phase, r["doppler"], r["carrier_phase"], r["peak"].real, r["start"], r["end"]))
     return np.array(rows)
+
+
+_WINDOW_CHILD = r"""
+import sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+from gypsum_b200 import _native
+from gypsum_b200.gps_ca_prn_codes import ca_code_chips
+n, nb = int(sys.argv[2]), int(sys.argv[3])
+x = np.load(sys.argv[4])
+e = _native.Engine(n * 1000, n)
+e.set_replicas(np.stack([ca_code_chips(sv) for sv in range(1, 33)]).astype(np.uint8))
+e.upload_iq(x)
+rec = e.acquire_grid(nb, 1, np.arange(32, dtype=np.int32), np.arange(-10000.0, 10001.0, 500.0))
+np.save(sys.argv[5], rec.view(np.uint8))
+e.close()
+"""
+
+
+@pytest.mark.parametrize("n, nb", [(2046, 20), (16368, 3)])
+def test_l2_windows_leave_every_record_unchanged(engine_for, tmp_path, n, nb):
+    """The one-warp kernel walks batches larger than L2 in windows of units (group order window / PRN / chunk, extra groups going
+    round the CTAs).  That only reorders independent cells: with windows forced onto a small batch (a child process, the knobs
+    are read once per process) every record is byte-identical to the single-window launch's, also with a ragged last window."""
+    import subprocess
+    import sys
+
+    rng = np.random.default_rng(n + nb)
+    x = (rng.standard_normal(2 * n * nb).astype(np.float32)).view(np.complex64)
+    x[:n] += o.synth_iq(0, n, 1, n * 1000, [(25, 1500.0, 777, 0.3, 0.3)], sigma=0.0)
+    e = engine_for(n)
+    e.upload_iq(x)
+    ref = e.acquire_grid(nb, 1, np.arange(32, dtype=np.int32), np.arange(-10000.0, 10001.0, 500.0))
+    assert int(ref["argmax"][0, 24, 23]) == 777
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    np.save(tmp_path / "x.npy", x)
+    for mb in ("1", "3"):
+        env = dict(os.environ, GB200_L2_WINDOW_MB=mb, GB200_L2_WINDOW_MIN_GROUPS="0")
+        subprocess.run([sys.executable, "-c", _WINDOW_CHILD, root, str(n), str(nb), str(tmp_path / "x.npy"), str(tmp_path / f"r{mb}.npy")],
+                       check=True, env=env, timeout=600)
+        got = np.load(tmp_path / f"r{mb}.npy")
+        assert np.array_equal(got, ref.view(np.uint8)), mb
