@@ -12,5 +12,5 @@ if [ "${2:-}" = "profile" ]; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_track_channels -s 1 -c 1 \
       -f -o gpurun_out/prof_track_${TAG} python tools/profile_tracker.py > gpurun_out/ncu_track_${TAG}.log 2>&1
 else
-  python bench.py --steps 200 --warmup 10 | tee gpurun_out/bench_${TAG}.json | cut -c1-1500
+  python bench.py | tee gpurun_out/bench_${TAG}.json | cut -c1-1500
 fi
