@@ -94,7 +94,9 @@ int gb200_acquire_grid_device(gb200_engine* e, int n_blocks, int ms_per_block, c
                               const double* doppler_hz, int n_doppler, int integration_type, void* out_device);
 /* The same grid host to host in ONE call for latency-bound callers (receiver.py:219-224 hands over one window per
  * scan): copy-in, both kernels and copy-out are replayed as one CUDA graph per grid shape, one host synchronisation.
- * iq_host: complex64[n_blocks * ms_per_block * N].                                                                    */
+ * iq_host: complex64[n_blocks * ms_per_block * N].  Pageable and pinned buffers are both accepted; with pinned ones
+ * (cudaHostAlloc / cudaHostRegister) inputs above 64 KB are read by the copy engine in place and small record sets
+ * (<= 256 KB) are stored by the kernel straight into out_host, which saves the two staging copies.                    */
 int gb200_acquire_grid_host(gb200_engine* e, const float* iq_host, int n_blocks, int ms_per_block, const int32_t* prn_idx,
                             int n_prn, const double* doppler_hz, int n_doppler, int integration_type,
                             gb200_cell_record* out_host);
