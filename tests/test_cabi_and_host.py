@@ -115,3 +115,46 @@ int main(void) {
     fields = [int(v) for v in out[0].split()]
     assert fields[0] == 2 and fields[1:5] == [32, 112, 32, 32]
     assert fields[5] == 0 or "no usable CUDA device" in out[1]
+
+
+def test_acquire_grid_host_wrapper_address_cache():
+    """Engine.acquire_grid_host keeps the addresses of the axis / record arrays only while the caller passes the very same
+    array objects and no converted copy was made; everything else is looked up again, and the shape check runs every time."""
+    from gypsum_b200 import _native
+
+    calls = []
+
+    class Lib:
+        def gb200_acquire_grid_host(self, h, iq, nb, m, p_prn, n_prn, p_dop, n_dop, kind, p_out):
+            calls.append((iq, nb, m, p_prn, n_prn, p_dop, n_dop, kind, p_out))
+            return 0
+
+    eng = object.__new__(_native.Engine)
+    eng._lib, eng._h, eng._host_call_cache, eng.samples_per_ms, eng.iq_tag = Lib(), None, None, 2046, "chunk"
+    prn = np.arange(4, dtype=np.int32)
+    dop = np.linspace(-1000.0, 1000.0, 5)
+    out = np.empty((1, 4, 5), dtype=_native.RECORD_DTYPE)
+    iq = np.zeros(2046, dtype=np.complex64)
+
+    assert eng.acquire_grid_host(iq, 1, 1, prn, dop, out=out) is out
+    assert eng.iq_tag is None  # the engine's IQ binding changed hands
+    assert calls[-1][3:7] == (prn.ctypes.data, 4, dop.ctypes.data, 5) and calls[-1][8] == out.ctypes.data
+    cached = eng._host_call_cache
+    assert cached is not None
+    eng.acquire_grid_host(iq.ctypes.data, 1, 1, prn, dop, out=out)  # same objects, IQ by address: served from the cache
+    assert eng._host_call_cache is cached and calls[-1][0] == iq.ctypes.data and calls[-1][8] == out.ctypes.data
+
+    out2 = np.empty((1, 4, 5), dtype=_native.RECORD_DTYPE)
+    eng.acquire_grid_host(iq, 1, 1, prn, dop, out=out2)  # another record buffer: looked up again
+    assert calls[-1][8] == out2.ctypes.data and eng._host_call_cache is not cached
+
+    eng.acquire_grid_host(iq, 1, 1, [0, 1, 2, 3], dop, out=out2)  # a list is converted to a temporary: nothing may be kept
+    assert eng._host_call_cache is None and calls[-1][4] == 4
+    made = eng.acquire_grid_host(iq, 1, 1, prn, dop)  # no buffer given: a fresh one each call, never cached
+    assert made.shape == (1, 4, 5) and eng._host_call_cache is None
+
+    eng.acquire_grid_host(iq, 1, 1, prn, dop, out=out)
+    with pytest.raises(ValueError):
+        eng.acquire_grid_host(iq, 2, 1, prn, dop, out=out)  # cached objects, wrong shape for this call
+    with pytest.raises(ValueError):
+        eng.acquire_grid_host(iq[:100], 1, 1, prn, dop, out=out)  # not enough samples
